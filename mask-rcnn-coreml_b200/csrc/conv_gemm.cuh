@@ -1,0 +1,348 @@
+// conv_gemm.cuh -- the dense hot op: NHWC fp16 convolution as an implicit GEMM on
+// the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by
+// TMA), used for every dense layer of the pipeline (ResNet+FPN+RPN backbone,
+// classifier head, mask head).
+//
+//   D[m, n] = sum_{tap, c}  X[pixel(m) + offset(tap), c] * W[n, tap, c]
+//
+//   M tile = a TH x TW rectangle of output pixels of one image (TH*TW = 128),
+//            loaded per filter tap as ONE 4-D TMA box (64 ch, TW, TH, 1) at the
+//            tap-shifted coordinate; out-of-image taps are zero-filled by TMA, so
+//            padding costs nothing and no im2col buffer exists.  Stride-2 layers
+//            use the tensor map's traversal strides.
+//   N tile = BN output channels; weights are a (Cout, taps*Cin) K-major matrix
+//            loaded as 2-D TMA boxes (64, BN).
+//   K step = 64 channels of one tap (128 B rows, SWIZZLE_128B on both operands).
+//
+// Persistent CTAs (one per SM), 6 warps:
+//   warp 0    TMA producer (one elected lane), NSTAGE-deep smem ring, mbarriers
+//   warp 1    tcgen05.mma issuer (one elected lane) + TMEM allocator
+//   warps 2-5 epilogue: tcgen05.ld (TMEM -> regs), + bias (+ residual, optionally
+//             nearest-2x-upsampled = the FPN top-down add) (+ ReLU), fp16 or fp32
+//             NHWC stores; optional 2x2 pixel-shuffle store (the mask head's
+//             stride-2 transposed conv).  Two TMEM accumulator stages, so the
+//             epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define CG_BM 128
+#define CG_BK 64
+#define CG_THREADS 192
+#define CG_MAX_TAPS 49
+
+struct ConvGemmParams {
+  int n_img, h_out, w_out;
+  int cout, ldc;               // valid output channels, output pixel stride (elements, multiple of 8)
+  int cin;                     // input channels per tap (multiple of 64)
+  int ntaps;
+  int tw, th;                  // tile rectangle, tw*th == 128
+  int tiles_x, tiles_y, tiles_n;
+  int stride;                  // spatial stride of the conv
+  int relu;
+  int out_f32;                 // 1: fp32 output
+  int res_mode;                // 0 none, 1 same resolution, 2 residual is half resolution (nearest 2x upsample)
+  int res_h, res_w, res_ld;
+  int deconv;                  // 1: cout = 4*deconv_c, output pixel (2y+dy, 2x+dx), channel c (2x2 stride-2 transposed conv)
+  int deconv_c;
+  const float* bias;           // [cout] or nullptr
+  const __half* residual;
+  void* out;
+  int8_t tap_dx[CG_MAX_TAPS];  // input offset of each tap, padding already subtracted
+  int8_t tap_dy[CG_MAX_TAPS];
+};
+
+namespace cg {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "CG_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra CG_DONE_%=;\n\t"
+      "bra CG_WAIT_%=;\n\t"
+      "CG_DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format):
+//  [0,14) start address >> 4, [16,30) LBO >> 4 (ignored for swizzled K-major, 1),
+//  [32,46) SBO >> 4 (8 rows * 128 B = 1024 B), [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor, kind::f16: D = F32 (bits 4-5 = 1), A = B = F16 (0), both K-major,
+// N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int BN> struct Cfg {
+  static constexpr int kABytes = CG_BM * CG_BK * 2;          // 16 KB
+  static constexpr int kBBytes = BN * CG_BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN >= 256) ? 4 : ((BN >= 128) ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // BN in {32,64,128,256} -> power of two
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+}  // namespace cg
+
+template <int BN>
+__global__ void __launch_bounds__(CG_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ ConvGemmParams p) {
+  using C = cg::Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-B aligned operand ring (SWIZZLE_128B requirement)
+  const uint32_t smem_base = (cg::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
+  // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - cg::smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + C::kStages * C::kStageBytes + 8 * (2 * C::kStages + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    cg::prefetch_tmap(&tmA);
+    cg::prefetch_tmap(&tmB);
+    for (int s = 0; s < C::kStages; ++s) { cg::mbar_init(full_bar(s), 1); cg::mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { cg::mbar_init(tfull_bar(a), 1); cg::mbar_init(tempty_bar(a), 4); }
+    cg::fence_barrier_init();
+  }
+  if (warp == 1) cg::tmem_alloc(tmem_slot, C::kTmemCols);
+  cg::tc_fence_before();
+  __syncthreads();
+  cg::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int tiles_m = p.n_img * p.tiles_y * p.tiles_x;
+  const int total_tiles = tiles_m * p.tiles_n;
+  const int cin_chunks = p.cin / CG_BK;
+  const int nkb = p.ntaps * cin_chunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_n;
+        const int mt = tile / p.tiles_n;
+        const int xt = mt % p.tiles_x;
+        const int yt = (mt / p.tiles_x) % p.tiles_y;
+        const int img = mt / (p.tiles_x * p.tiles_y);
+        const int x0 = xt * p.tw * p.stride, y0 = yt * p.th * p.stride;
+        const int n0 = nt * BN;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int xi = x0 + p.tap_dx[t], yi = y0 + p.tap_dy[t];
+          for (int cc = 0; cc < cin_chunks; ++cc) {
+            cg::mbar_wait(empty_bar(stage), phase ^ 1u);
+            cg::mbar_expect_tx(full_bar(stage), (uint32_t)C::kStageBytes);
+            const uint32_t a_dst = smem_base + stage * C::kStageBytes;
+            const uint32_t b_dst = a_dst + C::kABytes;
+            cg::tma_load_4d(a_dst, &tmA, full_bar(stage), cc * CG_BK, xi, yi, img);
+            cg::tma_load_2d(b_dst, &tmB, full_bar(stage), t * p.cin + cc * CG_BK, n0);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = cg::make_idesc_f16(CG_BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        cg::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);     // epilogue has drained this accumulator
+        cg::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          cg::mbar_wait(full_bar(stage), phase);              // TMA bytes have landed
+          cg::tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * C::kStageBytes;
+          const uint64_t adesc = cg::make_sw128_desc(a_addr);
+          const uint64_t bdesc = cg::make_sw128_desc(a_addr + C::kABytes);
+          #pragma unroll
+          for (int k = 0; k < CG_BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128-B swizzle atom: +2 in 16-B units
+            cg::umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          }
+          cg::umma_commit(empty_bar(stage));                   // frees the smem slot when the MMAs retire
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
+        cg::umma_commit(tfull_bar(acc));                       // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;          // accumulator row = pixel inside the tile
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.tiles_n;
+      const int mt = tile / p.tiles_n;
+      const int xt = mt % p.tiles_x;
+      const int yt = (mt / p.tiles_x) % p.tiles_y;
+      const int img = mt / (p.tiles_x * p.tiles_y);
+      const int x = xt * p.tw + (row % p.tw);
+      const int y = yt * p.th + (row / p.tw);
+      const bool pix_ok = (x < p.w_out) && (y < p.h_out);
+      const int n0 = nt * BN;
+      cg::mbar_wait(tfull_bar(acc), acc_phase);
+      cg::tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+
+      // output / residual row pointers
+      size_t out_off;
+      int ch_base = n0;
+      if (p.deconv) {
+        const int sub = n0 / p.deconv_c;               // BN divides deconv_c or vice versa is enforced by the host
+        const int dy = sub >> 1, dx = sub & 1;
+        out_off = (((size_t)img * (2 * p.h_out) + (2 * y + dy)) * (size_t)(2 * p.w_out) + (2 * x + dx)) * (size_t)p.ldc;
+        ch_base = n0 - sub * p.deconv_c;
+      } else {
+        out_off = (((size_t)img * p.h_out + y) * (size_t)p.w_out + x) * (size_t)p.ldc;
+      }
+      const __half* res_row = nullptr;
+      if (p.res_mode && pix_ok) {
+        const int ry = (p.res_mode == 2) ? (y >> 1) : y;
+        const int rx = (p.res_mode == 2) ? (x >> 1) : x;
+        res_row = p.residual + (((size_t)img * p.res_h + ry) * (size_t)p.res_w + rx) * (size_t)p.res_ld;
+      }
+      #pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        const int nc = n0 + chunk * 32;                 // first output channel of this chunk
+        if (nc >= p.ldc && !p.deconv) break;            // warp-uniform
+        uint32_t v[32];
+        cg::tmem_ld32(t_addr + (uint32_t)(chunk * 32), v);
+        cg::tmem_ld_wait();
+        if (pix_ok) {
+          #pragma unroll
+          for (int g = 0; g < 4; ++g) {                 // 4 groups of 8 channels
+            const int n = nc + g * 8;
+            const int cdst = ch_base + chunk * 32 + g * 8;
+            if (!p.deconv && n >= p.ldc) break;
+            float f[8];
+            #pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
+            if (p.bias) {
+              #pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] += (n + e < p.cout) ? __ldg(p.bias + n + e) : 0.0f;
+            }
+            if (res_row) {
+              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_row + n));
+              const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+              #pragma unroll
+              for (int e = 0; e < 4; ++e) { float2 r2 = __half22float2(rh[e]); f[2 * e] += r2.x; f[2 * e + 1] += r2.y; }
+            }
+            if (p.relu) {
+              #pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
+            }
+            if (p.out_f32) {
+              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + cdst);
+              o[0] = make_float4(f[0], f[1], f[2], f[3]);
+              o[1] = make_float4(f[4], f[5], f[6], f[7]);
+            } else {
+              uint4 ov;
+              __half2* oh = reinterpret_cast<__half2*>(&ov);
+              #pragma unroll
+              for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + out_off + cdst) = ov;
+            }
+          }
+        }
+      }
+      cg::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) cg::mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  // teardown
+  cg::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    cg::tc_fence_after();
+    cg::tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}

@@ -1,0 +1,159 @@
+// dense.cu -- host side of the tcgen05 implicit-GEMM convolution (conv_gemm.cuh):
+// TMA tensor-map construction, tile-shape selection and launch.
+#include "dense.h"
+#include <string.h>
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiled)p;
+  }
+  return fn;
+}
+
+template <int BN>
+static int launch_bn(mrcnn_ctx* ctx, const ConvPlan& plan) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    MRCNN_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             cg::Cfg<BN>::kSmemBytes));
+    attr_done = true;
+  }
+  conv_gemm_kernel<BN><<<plan.grid, CG_THREADS, cg::Cfg<BN>::kSmemBytes, ctx->stream>>>(plan.tmA, plan.tmB, plan.p);
+  MRCNN_LAUNCH_CHECK(ctx);
+  return MRCNN_OK;
+}
+
+int conv_plan_run(mrcnn_ctx* ctx, const ConvPlan& plan) {
+  switch (plan.bn) {
+    case 32: return launch_bn<32>(ctx, plan);
+    case 64: return launch_bn<64>(ctx, plan);
+    case 128: return launch_bn<128>(ctx, plan);
+    case 256: return launch_bn<256>(ctx, plan);
+  }
+  return mrcnn_fail(ctx, MRCNN_EINVAL, "conv: unsupported BN");
+}
+
+int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan) {
+  PFN_tmapEncodeTiled enc = get_encode_fn();
+  if (!enc) return mrcnn_fail(ctx, MRCNN_ECUDA, "conv: cuTensorMapEncodeTiled not available from the driver");
+  MRCNN_REQUIRE(ctx, L.x && L.w && L.out, "conv: null pointer");
+  MRCNN_REQUIRE(ctx, L.cin >= 64 && L.cin % 64 == 0, "conv: cin must be a multiple of 64");
+  const int ld_in = L.ld_in ? L.ld_in : L.cin;
+  MRCNN_REQUIRE(ctx, ld_in % 8 == 0, "conv: input pixel stride must be a multiple of 8 elements");
+  const int ntaps = L.ntaps_override ? L.ntaps_override : L.kh * L.kw;
+  MRCNN_REQUIRE(ctx, ntaps >= 1 && ntaps <= CG_MAX_TAPS, "conv: too many taps");
+  MRCNN_REQUIRE(ctx, L.stride == 1 || L.stride == 2, "conv: stride must be 1 or 2");
+  ConvGemmParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  p.n_img = L.n;
+  p.h_out = L.h_out ? L.h_out : (L.h_in + 2 * L.pad - L.kh) / L.stride + 1;
+  p.w_out = L.w_out ? L.w_out : (L.w_in + 2 * L.pad - L.kw) / L.stride + 1;
+  MRCNN_REQUIRE(ctx, p.h_out >= 1 && p.w_out >= 1, "conv: empty output");
+  p.cout = L.cout;
+  p.ldc = L.ldc ? L.ldc : ((L.deconv ? L.deconv_c : L.cout) + 7) / 8 * 8;
+  MRCNN_REQUIRE(ctx, p.ldc % 8 == 0, "conv: ldc must be a multiple of 8");
+  p.cin = L.cin;
+  p.ntaps = ntaps;
+  if (L.tw && L.th) { p.tw = L.tw; p.th = L.th; }
+  else if (p.h_out == 1) { p.tw = 128; p.th = 1; }
+  else if (p.w_out > 8) { p.tw = 16; p.th = 8; }
+  else { p.tw = 8; p.th = 16; }
+  MRCNN_REQUIRE(ctx, p.tw * p.th == CG_BM, "conv: tile must cover 128 pixels");
+  MRCNN_REQUIRE(ctx, p.tw * L.stride <= 256 && p.th * L.stride <= 256, "conv: TMA box too large");
+  p.tiles_x = ceil_div(p.w_out, p.tw);
+  p.tiles_y = ceil_div(p.h_out, p.th);
+  int bn = L.bn;
+  if (!bn) bn = L.cout > 128 ? 256 : (L.cout > 64 ? 128 : (L.cout > 32 ? 64 : 32));
+  MRCNN_REQUIRE(ctx, bn == 32 || bn == 64 || bn == 128 || bn == 256, "conv: BN must be 32/64/128/256");
+  if (L.deconv) MRCNN_REQUIRE(ctx, L.deconv_c % bn == 0 && L.cout == 4 * L.deconv_c, "conv: deconv needs deconv_c % BN == 0");
+  p.tiles_n = ceil_div(L.cout, bn);
+  p.stride = L.stride;
+  p.relu = L.relu; p.out_f32 = L.out_f32;
+  p.res_mode = L.residual ? L.res_mode : 0;
+  p.res_h = L.res_h ? L.res_h : p.h_out; p.res_w = L.res_w ? L.res_w : p.w_out;
+  p.res_ld = L.res_ld ? L.res_ld : p.ldc;
+  p.deconv = L.deconv; p.deconv_c = L.deconv_c;
+  p.bias = L.bias; p.residual = L.residual; p.out = L.out;
+  if (L.ntaps_override) {
+    for (int t = 0; t < ntaps; ++t) { p.tap_dx[t] = L.tap_dx[t]; p.tap_dy[t] = L.tap_dy[t]; }
+  } else {
+    for (int ky = 0; ky < L.kh; ++ky)
+      for (int kx = 0; kx < L.kw; ++kx) {
+        p.tap_dy[ky * L.kw + kx] = (int8_t)(ky - L.pad);
+        p.tap_dx[ky * L.kw + kx] = (int8_t)(kx - L.pad);
+      }
+  }
+  plan->bn = bn;
+  const long total_tiles = (long)p.n_img * p.tiles_x * p.tiles_y * p.tiles_n;
+  plan->grid = (int)(total_tiles < ctx->sm_count ? total_tiles : ctx->sm_count);
+  plan->flops = 2.0 * p.n_img * p.h_out * p.w_out * (double)L.cout * ntaps * L.cin;
+
+  // ---- A: 4-D (C, W, H, N) view of the NHWC activation, box (64, tw*s, th*s, 1), traversal stride s
+  cuuint64_t adims[4], astr[3];
+  if (L.custom_view) {
+    for (int i = 0; i < 4; ++i) adims[i] = L.a_dims[i];
+    for (int i = 0; i < 3; ++i) astr[i] = L.a_strides[i];
+  } else {
+    adims[0] = (cuuint64_t)L.cin; adims[1] = (cuuint64_t)L.w_in; adims[2] = (cuuint64_t)L.h_in; adims[3] = (cuuint64_t)L.n;
+    astr[0] = (cuuint64_t)ld_in * 2; astr[1] = astr[0] * L.w_in; astr[2] = astr[1] * L.h_in;
+  }
+  cuuint32_t abox[4] = {(cuuint32_t)CG_BK, (cuuint32_t)(p.tw * L.stride), (cuuint32_t)(p.th * L.stride), 1};
+  cuuint32_t aes[4] = {1, (cuuint32_t)L.stride, (cuuint32_t)L.stride, 1};
+  CUresult r = enc(&plan->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)L.x, adims, astr, abox, aes,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[256];
+    snprintf(b, sizeof(b), "conv: cuTensorMapEncodeTiled(A) failed with %d (dims %llu,%llu,%llu,%llu)", (int)r,
+             (unsigned long long)adims[0], (unsigned long long)adims[1], (unsigned long long)adims[2], (unsigned long long)adims[3]);
+    return mrcnn_fail(ctx, MRCNN_ECUDA, b);
+  }
+  // ---- B: 2-D (K, Cout) K-major weights, box (64, BN)
+  cuuint64_t bdims[2] = {(cuuint64_t)ntaps * L.cin, (cuuint64_t)L.cout};
+  cuuint64_t bstr[1] = {(cuuint64_t)ntaps * L.cin * 2};
+  cuuint32_t bbox[2] = {(cuuint32_t)CG_BK, (cuuint32_t)bn};
+  cuuint32_t bes[2] = {1, 1};
+  r = enc(&plan->tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)L.w, bdims, bstr, bbox, bes,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[128];
+    snprintf(b, sizeof(b), "conv: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+    return mrcnn_fail(ctx, MRCNN_ECUDA, b);
+  }
+  return MRCNN_OK;
+}
+
+extern "C" {
+
+// Test / bench hook: one NHWC fp16 convolution through the tcgen05 kernel.
+//   x [n,h,w,cin] f16, wgt [cout,kh,kw,cin] f16, bias [cout] f32 or NULL,
+//   residual [n,h_out,w_out,cout] f16 or NULL, out [n,h_out,w_out,round_up(cout,8)] f16.
+// Device pointers only.
+MRCNN_API int mrcnn_conv2d_nhwc_f16(mrcnn_ctx* ctx, const void* x, int n, int h, int w, int cin, const void* wgt,
+                                    const float* bias, int cout, int kh, int kw, int stride, int pad,
+                                    const void* residual, int relu, void* out) {
+  if (!ctx) return MRCNN_EINVAL;
+  cudaSetDevice(ctx->device);
+  ConvLaunch L;
+  L.x = (const __half*)x; L.n = n; L.h_in = h; L.w_in = w; L.cin = cin;
+  L.w = (const __half*)wgt; L.cout = cout; L.kh = kh; L.kw = kw; L.stride = stride; L.pad = pad;
+  L.bias = bias; L.residual = (const __half*)residual; L.res_mode = residual ? 1 : 0;
+  L.relu = relu; L.out = out;
+  ConvPlan plan;
+  int rc = conv_plan_build(ctx, L, &plan);
+  if (rc) return rc;
+  return conv_plan_run(ctx, plan);
+}
+
+}  // extern "C"

@@ -1,0 +1,45 @@
+// dense.h -- interface between the C ABI (api.cu) and the dense model
+// (dense.cu: tcgen05 implicit-GEMM convolution plans; pipeline.cu: the model).
+#pragma once
+#include "common.cuh"
+#include "conv_gemm.cuh"
+
+// One convolution (or GEMM) as the caller sees it.  Activations are NHWC fp16.
+struct ConvLaunch {
+  const __half* x = nullptr;
+  int n = 1, h_in = 1, w_in = 1, cin = 64;
+  int ld_in = 0;                 // input pixel stride in elements (0 -> cin)
+  // optional explicit A view (overrides the NHWC view): dims fastest-first and byte strides of dims 1..3
+  bool custom_view = false;
+  uint64_t a_dims[4] = {0, 0, 0, 0};
+  uint64_t a_strides[3] = {0, 0, 0};
+  const __half* w = nullptr;     // [cout][ntaps*cin] K-major, taps ordered (ky, kx)
+  int cout = 64;
+  int kh = 1, kw = 1, stride = 1, pad = 0;
+  int ntaps_override = 0;        // custom tap list (conv1 space-to-depth view)
+  int8_t tap_dx[CG_MAX_TAPS] = {0};
+  int8_t tap_dy[CG_MAX_TAPS] = {0};
+  const float* bias = nullptr;
+  const __half* residual = nullptr;
+  int res_mode = 0, res_h = 0, res_w = 0, res_ld = 0;
+  int relu = 0, out_f32 = 0, deconv = 0, deconv_c = 0;
+  void* out = nullptr;
+  int h_out = 0, w_out = 0;      // 0 -> derived from kh/kw/stride/pad
+  int ldc = 0;                   // 0 -> round_up(cout, 8)
+  int tw = 0, th = 0, bn = 0;    // 0 -> auto
+};
+
+struct ConvPlan {
+  CUtensorMap tmA, tmB;
+  ConvGemmParams p;
+  int bn = 0, grid = 0;
+  size_t smem = 0;
+  double flops = 0;
+};
+
+int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan);
+int conv_plan_run(mrcnn_ctx* ctx, const ConvPlan& plan);
+
+int dense_load_weights(mrcnn_ctx* ctx, int which, const void* blob, size_t bytes);
+void dense_destroy(mrcnn_ctx* ctx);
+void comm_destroy(mrcnn_ctx* ctx);
