@@ -298,7 +298,6 @@ int proposal_run(mrcnn_ctx* ctx, int batch, int64_t N, const float* d_probs, con
                                                   ctx->d_cand, cand_stride);
   MRCNN_LAUNCH_CHECK(ctx);
   float4 sd = make_float4(cfg.bbox_std[0], cfg.bbox_std[1], cfg.bbox_std[2], cfg.bbox_std[3]);
-  size_t sort_smem = sizeof(unsigned long long) * (size_t)sort_n;
 #define LAUNCH_SORT(SN)                                                                          \
   do {                                                                                           \
     static bool attr_set_##SN = false;                                                           \
@@ -308,7 +307,7 @@ int proposal_run(mrcnn_ctx* ctx, int batch, int64_t N, const float* d_probs, con
                                                (int)(sizeof(unsigned long long) * SN)));         \
       attr_set_##SN = true;                                                                      \
     }                                                                                            \
-    sort_decode_kernel<SN><<<batch, 1024, sort_smem, s>>>(                                       \
+    sort_decode_kernel<SN><<<batch, 1024, sizeof(unsigned long long) * SN, s>>>(                                       \
         ctx->d_cand, cand_stride, pre, idx_bits, N, (const float4*)d_deltas,                     \
         (const float4*)ctx->d_anchors, sd, ctx->d_sboxes, ctx->d_sorder, stride);                \
   } while (0)

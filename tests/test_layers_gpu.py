@@ -1,0 +1,231 @@
+"""GPU parity tests: every custom layer through the C ABI (ctypes) against the CPU
+oracle on the same seeded inputs.  Bit-exact for keep indices / class ids /
+levels; boxes and ROIAlign values are compared exactly too (the arithmetic
+contract makes them bit-identical; the north-star tolerance is 1e-4)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4   # north-star tolerance for boxes / masks / pooled features
+
+
+@pytest.fixture(scope="module")
+def anchors(pkg):
+    return pkg.synth.generate_anchors(1024, 1024)
+
+
+def test_anchor_count(anchors):
+    assert anchors.shape == (261888, 4)
+
+
+def _run_proposal(pkg, ctx, probs, deltas):
+    b = probs.shape[0]
+    mp = ctx.cfg.max_proposals
+    rois = np.full((b, mp, 4), 7.0, np.float32)          # poisoned: every element must be written
+    keep = np.full((b, mp), 99, np.int32)
+    cnt = np.zeros(b, np.int32)
+    pkg.ProposalLayer(context=ctx).evaluate([probs, deltas], [rois], keep_anchor=keep, count=cnt)
+    return rois, keep, cnt
+
+
+def test_proposal_full_size_batch(pkg, ctx, orc, anchors):
+    ctx.set_anchors(anchors)
+    imgs = [pkg.synth.rpn_outputs(anchors, i) for i in range(3)]
+    probs = np.stack([p for p, _ in imgs])
+    deltas = np.stack([d for _, d in imgs])
+    rois, keep, cnt = _run_proposal(pkg, ctx, probs, deltas)
+    for i in range(3):
+        r0, k0, c0 = orc.proposal(probs[i], deltas[i], anchors)
+        assert cnt[i] == c0
+        np.testing.assert_array_equal(keep[i], k0)            # bit-exact NMS keep indices
+        np.testing.assert_allclose(rois[i], r0, rtol=0, atol=TOL)
+        np.testing.assert_array_equal(rois[i], r0)
+        assert c0 == 1000                                     # the synthetic RPN fills all proposals
+
+
+def test_proposal_ties_and_small_n(pkg, orc):
+    # duplicated scores (tie order = lower anchor first), fewer anchors than pre_nms, <max survivors (Q4)
+    c = pkg.Context(pre_nms_max_proposals=300, max_proposals=50)
+    rng = np.random.default_rng(11)
+    n = 1000
+    a = pkg.synth.random_rois(n, 5, min_px=30, max_px=300)
+    c.set_anchors(a)
+    probs = np.zeros((1, n, 2), np.float32)
+    probs[0, :, 1] = rng.integers(0, 20, n).astype(np.float32) / 20.0     # heavy ties
+    probs[0, :, 0] = 1 - probs[0, :, 1]
+    deltas = (rng.standard_normal((1, n, 4)) * 0.3).astype(np.float32)
+    rois = np.zeros((1, 50, 4), np.float32); keep = np.zeros((1, 50), np.int32); cnt = np.zeros(1, np.int32)
+    pkg.ProposalLayer({"preNMSMaxProposals": 300, "maxProposals": 50}, context=c).evaluate([probs, deltas], [rois], keep, cnt)
+    r0, k0, c0 = orc.proposal(probs[0], deltas[0], a, pre_nms=300, max_proposals=50)
+    assert cnt[0] == c0
+    np.testing.assert_array_equal(keep[0], k0)
+    np.testing.assert_array_equal(rois[0], r0)
+    # all scores equal: the first 300 anchors by index are the candidates
+    probs[0, :, 1] = 0.5
+    pkg.ProposalLayer({"preNMSMaxProposals": 300, "maxProposals": 50}, context=c).evaluate([probs, deltas], [rois], keep, cnt)
+    r0, k0, c0 = orc.proposal(probs[0], deltas[0], a, pre_nms=300, max_proposals=50)
+    np.testing.assert_array_equal(keep[0], k0)
+    assert k0[:c0].max() < 300
+    # N < pre_nms and fewer survivors than max (the reference would trap here, Q4)
+    c2 = pkg.Context(pre_nms_max_proposals=6000, max_proposals=1000)
+    small = np.tile(np.array([[0.1, 0.1, 0.6, 0.6]], np.float32), (40, 1))
+    small[:, 1] += np.arange(40, dtype=np.float32) * 1e-4
+    c2.set_anchors(small)
+    p = np.zeros((1, 40, 2), np.float32); p[0, :, 1] = np.linspace(0.1, 0.9, 40)
+    d = np.zeros((1, 40, 4), np.float32)
+    rois = np.ones((1, 1000, 4), np.float32); keep = np.zeros((1, 1000), np.int32); cnt = np.zeros(1, np.int32)
+    pkg.ProposalLayer(context=c2).evaluate([p, d], [rois], keep, cnt)
+    r0, k0, c0 = orc.proposal(p[0], d[0], small)
+    assert cnt[0] == c0 == 1
+    np.testing.assert_array_equal(keep[0], k0)
+    np.testing.assert_array_equal(rois[0], r0)
+    c.close(); c2.close()
+
+
+def test_proposal_zero_area_boxes(pkg, orc):
+    c = pkg.Context(pre_nms_max_proposals=64, max_proposals=16)
+    a = pkg.synth.random_rois(64, 9, min_px=50, max_px=200)
+    a[::3, 2] = a[::3, 0]                                   # zero height -> never selectable (Utils.swift:195)
+    c.set_anchors(a)
+    rng = np.random.default_rng(2)
+    p = np.zeros((1, 64, 2), np.float32); p[0, :, 1] = rng.uniform(size=64)
+    d = np.zeros((1, 64, 4), np.float32)
+    rois = np.zeros((1, 16, 4), np.float32); keep = np.zeros((1, 16), np.int32); cnt = np.zeros(1, np.int32)
+    pkg.ProposalLayer({"preNMSMaxProposals": 64, "maxProposals": 16}, context=c).evaluate([p, d], [rois], keep, cnt)
+    r0, k0, c0 = orc.proposal(p[0], d[0], a, pre_nms=64, max_proposals=16)
+    np.testing.assert_array_equal(keep[0], k0)
+    np.testing.assert_array_equal(rois[0], r0)
+    assert not np.isin(k0[:c0], np.arange(0, 64, 3)).any()
+    c.close()
+
+
+@pytest.mark.parametrize("pool,stride", [(7, 4), (14, 6)])
+def test_pyramid_roialign_boundary_layout(pkg, ctx, orc, pool, stride):
+    b, r, ch = 2, 200, 32
+    maps = [np.stack([pkg.synth.feature_maps(i, channels=ch)[l] for i in range(b)]) for l in range(4)]
+    rois = np.zeros((b, r, stride), np.float32)
+    for i in range(b):
+        rois[i, :, :4] = pkg.synth.random_rois(r, i, n_pad=7)
+        rois[i, 5, :4] = [0.2, 0.3, 0.2, 0.5]                 # zero-height roi -> padding block
+    out = np.full((b, r, ch, pool, pool), 3.0, np.float32)
+    lv = np.zeros((b, r), np.int32)
+    pkg.PyramidROIAlignLayer({"poolSize": pool}, context=ctx).evaluate([rois] + maps, [out], level=lv)
+    for i in range(b):
+        o0, l0 = orc.pyramid_roialign(rois[i], [m[i] for m in maps], pool)
+        np.testing.assert_array_equal(lv[i], l0)
+        np.testing.assert_allclose(out[i], o0, rtol=0, atol=TOL)
+        np.testing.assert_array_equal(out[i], o0)
+        assert set(np.unique(l0)) >= {-1, 2, 3, 4, 5}
+        assert not out[i, r - 7:].any() and not out[i, 5].any()
+
+
+def test_pyramid_roialign_nhwc_f16(pkg, ctx, orc):
+    import ctypes as C
+    import torch
+    b, r, ch, pool = 2, 150, 256, 7
+    maps = [np.stack([pkg.synth.feature_maps(10 + i, channels=ch)[l] for i in range(b)]) for l in range(4)]
+    hwc = [np.ascontiguousarray(m.transpose(0, 2, 3, 1)).astype(np.float16) for m in maps]
+    rois = np.stack([pkg.synth.random_rois(r, 20 + i, n_pad=3) for i in range(b)])
+    d_maps = [torch.from_numpy(m).cuda() for m in hwc]
+    d_rois = torch.from_numpy(rois).cuda()
+    d_out = torch.full((b, r, pool, pool, ch), 5.0, dtype=torch.float16, device="cuda")
+    d_lv = torch.zeros((b, r), dtype=torch.int32, device="cuda")
+    hw = (C.c_int32 * 8)(*[d for m in hwc for d in m.shape[1:3]])
+    fp = (C.c_void_p * 4)(*[m.data_ptr() for m in d_maps])
+    pkg._cabi.check(ctx.handle, pkg.lib().mrcnn_roialign_nhwc_f16(ctx.handle, b, d_rois.data_ptr(), 4, r, fp, hw, ch, pool,
+                                                               d_out.data_ptr(), d_lv.data_ptr()))
+    ctx.synchronize()
+    out = d_out.cpu().numpy(); lv = d_lv.cpu().numpy()
+    for i in range(b):
+        o0, l0 = orc.pyramid_roialign_nhwc_f16(rois[i], [m[i] for m in hwc], pool)
+        np.testing.assert_array_equal(lv[i], l0)
+        np.testing.assert_array_equal(out[i].view(np.uint16), o0.view(np.uint16))      # bit-exact fp16
+
+
+def test_classifier_select(pkg, ctx, orc):
+    probs = np.stack([pkg.synth.classifier_outputs(500, i)[0] for i in range(2)])
+    bbox = np.stack([pkg.synth.classifier_outputs(500, i)[1] for i in range(2)])
+    probs[0, 3, 5] = probs[0, 3, 9] = 0.99                     # tie -> first max (Q7)
+    out = np.zeros((2, 500, 6), np.float32)
+    pkg.TimeDistributedClassifierLayer(context=ctx).select(probs, bbox, out)
+    for i in range(2):
+        np.testing.assert_array_equal(out[i], orc.classifier_select(probs[i], bbox[i]))
+    assert out[0, 3, 4] == 5
+
+
+def _cls_from_synth(pkg, orc, r, seed):
+    p, bb = pkg.synth.classifier_outputs(r, seed)
+    return orc.classifier_select(p, bb)
+
+
+def test_detection_layer(pkg, ctx, orc):
+    b, r = 3, 1000
+    rois = np.stack([pkg.synth.random_rois(r, 40 + i, min_px=20, max_px=500) for i in range(b)])
+    cls = np.stack([_cls_from_synth(pkg, orc, r, 40 + i) for i in range(b)])
+    cls[..., :4] *= 0.5
+    # image 2: heavy clustering so per-class NMS really suppresses, plus score ties
+    rois[2, 100:400] = rois[2, 100] + (np.random.default_rng(3).uniform(-0.01, 0.01, (300, 4))).astype(np.float32)
+    rois[2] = np.clip(rois[2], 0, 1)
+    cls[2, 100:400, 4] = 3.0
+    cls[2, 100:400, 5] = np.float32(0.9)
+    out = np.full((b, 100, 6), 9.0, np.float32); keep = np.zeros((b, 100), np.int32); cnt = np.zeros(b, np.int32)
+    pkg.DetectionLayer(context=ctx).evaluate([rois, cls], [out], keep_roi=keep, count=cnt)
+    for i in range(b):
+        o0, k0, c0 = orc.detection(rois[i], cls[i])
+        assert cnt[i] == c0
+        np.testing.assert_array_equal(keep[i], k0)             # bit-exact keep indices
+        np.testing.assert_array_equal(out[i, :, 4], o0[:, 4])  # bit-exact class ids
+        np.testing.assert_allclose(out[i], o0, rtol=0, atol=TOL)
+        np.testing.assert_array_equal(out[i], o0)
+    assert cnt.max() == 100
+
+
+def test_detection_layer_edges(pkg, ctx, orc):
+    r = 64
+    rois = pkg.synth.random_rois(r, 77)[None]
+    cls = np.zeros((1, r, 6), np.float32)
+    out = np.ones((1, 100, 6), np.float32); keep = np.zeros((1, 100), np.int32); cnt = np.ones(1, np.int32)
+    pkg.DetectionLayer(context=ctx).evaluate([rois, cls], [out], keep, cnt)     # nothing passes
+    assert cnt[0] == 0 and not out.any() and (keep == -1).all()
+    cls[0, :, 4] = 1; cls[0, :, 5] = np.float32(0.7)                             # == threshold: kept (Q8)
+    cls[0, 10, 5] = np.nextafter(np.float32(0.7), np.float32(0))
+    pkg.DetectionLayer(context=ctx).evaluate([rois, cls], [out], keep, cnt)
+    o0, k0, c0 = orc.detection(rois[0], cls[0])
+    assert cnt[0] == c0 and 10 not in keep[0]
+    np.testing.assert_array_equal(keep[0], k0)
+    np.testing.assert_array_equal(out[0], o0)
+
+
+def test_detections_decode(pkg, ctx, orc):
+    import ctypes as C
+    rng = np.random.default_rng(8)
+    det = np.zeros((2, 100, 6), np.float32)
+    det[:, :30, :4] = np.sort(rng.uniform(size=(2, 30, 4)).astype(np.float32), axis=-1)[..., [0, 1, 2, 3]]
+    det[:, :30, 4] = rng.integers(1, 81, (2, 30))
+    det[:, :30, 5] = rng.uniform(0.6, 1.0, (2, 30))
+    det[0, 3, 5] = np.float32(0.7)
+    masks = rng.uniform(size=(2, 100, 28, 28)).astype(np.float32)
+    cnt = np.zeros(2, np.int32); idx = np.zeros((2, 100), np.int32); bbox = np.zeros((2, 100, 4), np.float64)
+    cls = np.zeros((2, 100), np.int32); score = np.zeros((2, 100), np.float64); mu8 = np.zeros((2, 100, 784), np.uint8)
+    P = pkg._cabi.ptr
+    pkg._cabi.check(ctx.handle, pkg.lib().mrcnn_detections_decode(ctx.handle, 2, P(det), P(masks), P(cnt), P(idx), P(bbox),
+                                                               P(cls), P(score), P(mu8)))
+    for i in range(2):
+        n0, i0, b0, c0, s0, m0 = orc.detections_decode(det[i], masks[i])
+        assert cnt[i] == n0
+        np.testing.assert_array_equal(idx[i, :n0], i0[:n0]); np.testing.assert_array_equal(cls[i, :n0], c0[:n0])
+        np.testing.assert_array_equal(bbox[i, :n0], b0[:n0]); np.testing.assert_array_equal(score[i, :n0], s0[:n0])
+        np.testing.assert_array_equal(mu8[i, :n0], m0[:n0])
+
+
+def test_error_paths(pkg, ctx):
+    rois = np.zeros((1, 1000, 4), np.float32)
+    with pytest.raises(pkg.MaskRCNNError):
+        # anchors for a different N
+        ctx.set_anchors(np.zeros((10, 4), np.float32))
+        pkg.ProposalLayer(context=ctx).evaluate([np.zeros((1, 20, 2), np.float32), np.zeros((1, 20, 4), np.float32)], [rois])
+    with pytest.raises(pkg.MaskRCNNError):
+        pkg.ProposalLayer({"maxProposals": 5}, context=ctx)     # parameters must match the context
+    with pytest.raises(pkg.MaskRCNNError):
+        pkg.Context(anchors_path="/nonexistent/anchors.bin")
