@@ -1,0 +1,489 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the Mask-RCNN hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload pipeline|custom_layers] [--batch B]
+
+One "step" = one pass of the hot path over one batch of synthetic 1024x1024
+inputs (BASELINE.json configs[1]: batch 8 per GPU, 6000 -> 1000 proposals).
+  value  : whole-job images/s, inputs already resident in HBM (device pointers
+           through the C ABI), CUDA-event timed, max over ranks.
+  e2e    : the same through the reference-facing call with HOST buffers (pinned),
+           host<->device copies inside the timed region.
+  roofline: the dominant kernel class, timed live with CUDA event pairs on the
+           library's stream (mrcnn_profile_*), against MEASURED_PEAKS.json.
+  cpu_baseline: the oracle (a port; the Swift reference cannot run on Linux) on a
+           bounded sample, rank 0 / N=1 only.
+--impl reference times that CPU path alone (all host threads it can use).
+Nothing here reads /root/reference.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec (1024x1024, 1000 ROIs)"
+UNIT = "images/s"
+IMG = 1024
+
+
+# --------------------------------------------------------------------------- utils
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": d["hbm_gbs"], "bf16": d["bf16_tflops"], "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm": 6650.0, "bf16": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# --------------------------------------------------------------------------- CPU legs (oracle)
+def cpu_custom_layers_image(orc, synth, anchors, image_index, maps):
+    """The reference's custom-layer path for ONE image on the CPU (oracle port): full argsort of
+    261,888 scores, sequential greedy NMS with double IoU, scalar crop-and-resize."""
+    probs, deltas = synth.rpn_outputs(anchors, image_index)
+    t0 = time.perf_counter()
+    rois, _, _ = orc.proposal(probs, deltas, anchors)
+    pooled, _ = orc.pyramid_roialign(rois, maps, 7)
+    pr, bb = synth.classifier_outputs(1000, image_index)
+    cls = orc.classifier_select(pr, bb)
+    det, _, _ = orc.detection(rois, cls)
+    pooled14, _ = orc.pyramid_roialign(det, maps, 14)
+    dt = time.perf_counter() - t0
+    return dt
+
+
+_CPU_STATE = {}
+
+
+def cpu_pipeline_image(m, orc, image_index, architecture=101, size=IMG):
+    """The reference's whole path for ONE image on the host CPU: dense graphs = oracle/dense_ref.py (PyTorch CPU
+    fp32, all host threads; what Core ML's CPU path does with the .mlmodel graphs), custom layers = oracle.c
+    (single thread, like the reference's Swift layers).  Returns (seconds, per-stage seconds)."""
+    import torch
+    from oracle.dense_ref import Ref
+    st = _CPU_STATE
+    if "ref" not in st:
+        folded, _ = m.weights.synthetic_blobs(architecture)
+        st["ref"] = Ref(folded, architecture, act_half=False, device="cpu")
+        st["anchors"] = m.synth.generate_anchors(size, size)
+    ref, anchors = st["ref"], st["anchors"]
+    rng = np.random.default_rng(20260 + image_index)
+    img = rng.integers(0, 256, (1, size, size, 3), dtype=np.uint8)
+    t = [time.perf_counter()]
+    with torch.no_grad():
+        fm, probs, deltas = ref.backbone(img)
+        t.append(time.perf_counter())
+        rois, _, _ = orc.proposal(probs[0].numpy(), deltas[0].numpy(), anchors)
+        t.append(time.perf_counter())
+        maps = [np.ascontiguousarray(f[0].permute(2, 0, 1).numpy()) for f in fm]      # CHW fp32, the layer's layout
+        pooled, _ = orc.pyramid_roialign(rois, maps, 7, size, size)
+        t.append(time.perf_counter())
+        pr, bb, _ = ref.classifier(np.ascontiguousarray(pooled.transpose(0, 2, 3, 1)))
+        cls = orc.classifier_select(pr.numpy(), bb.numpy())
+        t.append(time.perf_counter())
+        det, _, n = orc.detection(rois, cls)
+        t.append(time.perf_counter())
+        pooled14, lv = orc.pyramid_roialign(det, maps, 14, size, size)
+        t.append(time.perf_counter())
+        nv = max(int((lv >= 0).sum()), 1)                # removeZeros: the Mask model only runs on valid blocks
+        mk = ref.mask(np.ascontiguousarray(pooled14[:nv].transpose(0, 2, 3, 1))).numpy()
+        full = np.zeros((100,) + mk.shape[1:], np.float32); full[:nv] = mk
+        orc.mask_select(full, (lv >= 0).astype(np.int32), det)
+        t.append(time.perf_counter())
+    names = ["backbone+fpn+rpn", "proposal", "roialign7", "classifier", "detection", "roialign14", "mask"]
+    return t[-1] - t[0], dict(zip(names, np.diff(t).tolist()))
+
+
+def run_reference(args):
+    """--impl reference: the CPU path of the reference for this workload, timed on the host cores."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    import maskrcnn_b200 as m
+    from oracle import oracle as orc
+    orc.lib()
+    cores = os.cpu_count() or 1
+    workload = args.workload
+    times = []
+    if workload == "pipeline":
+        import torch
+        torch.set_num_threads(cores)
+        for s in range(args.warmup + args.steps):
+            dt, _ = cpu_pipeline_image(m, orc, s)
+            if s >= args.warmup:
+                times.append(dt)
+        sample = ("1 image (1024x1024, ResNet101+FPN, 1000 rois) per step: PyTorch-CPU fp32 dense graphs on all host "
+                  "threads + oracle.c custom layers (1 thread)")
+        kind_cores = cores
+    else:
+        workload = "custom_layers"
+        anchors = m.synth.generate_anchors(IMG, IMG)
+        maps = m.synth.feature_maps(0)
+        for s in range(args.warmup + args.steps):
+            dt = cpu_custom_layers_image(orc, m.synth, anchors, s, maps)
+            if s >= args.warmup:
+                times.append(dt)
+        sample = "1 image per step: oracle custom layers (single thread, like the reference's layers)"
+        kind_cores = 1
+    ms = 1e3 * float(np.mean(times))
+    v = 1e3 / ms
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": workload, "image": "1024x1024", "rois": 1000},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": kind_cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# --------------------------------------------------------------------------- GPU workloads
+class CustomLayersWorkload:
+    """The five custom layers of the reference on synthetic RPN outputs / feature maps (no dense
+    graph): ProposalLayer -> PyramidROIAlign(7) -> classifier select -> DetectionLayer ->
+    PyramidROIAlign(14) -> Detection decode.  Layer-level ABI, reference (CHW fp32) layouts."""
+    name = "custom_layers"
+    dtype = "f32"
+
+    def __init__(self, m, torch, device, batch, seed_base):
+        self.m, self.torch, self.b = m, torch, batch
+        self.ctx = m.Context(device=device, max_batch=batch)
+        self.stream = torch.cuda.Stream()
+        self.ctx.set_stream(self.stream.cuda_stream)
+        anchors = m.synth.generate_anchors(IMG, IMG)
+        self.ctx.set_anchors(anchors)
+        # two distinct images' worth of RPN outputs, tiled (generation is slow on the host)
+        gen = [m.synth.rpn_outputs(anchors, seed_base + i) for i in range(min(batch, 2))]
+        probs = np.stack([gen[i % len(gen)][0] for i in range(batch)])
+        deltas = np.stack([gen[i % len(gen)][1] for i in range(batch)])
+        cls = [m.synth.classifier_outputs(1000, seed_base + i) for i in range(min(batch, 2))]
+        cprob = np.stack([cls[i % len(cls)][0] for i in range(batch)])
+        cbbox = np.stack([cls[i % len(cls)][1] for i in range(batch)])
+        pin = lambda a: torch.from_numpy(a).pin_memory()
+        self.h = {"probs": pin(probs), "deltas": pin(deltas), "cprob": pin(cprob), "cbbox": pin(cbbox)}
+        g = torch.Generator(device="cuda").manual_seed(20260 + seed_base)
+        self.d_maps = [torch.randn((batch, 256, IMG // s, IMG // s), device="cuda", generator=g) for s in (4, 8, 16, 32)]
+        self.h_maps = None
+        self.d = {k: v.cuda() for k, v in self.h.items()}
+        z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device="cuda")
+        self.out = {"rois": z(batch, 1000, 4), "pooled": z(batch, 1000, 256, 7, 7), "cls": z(batch, 1000, 6),
+                    "det": z(batch, 100, 6), "pooled14": z(batch, 100, 256, 14, 14),
+                    "cnt": z(batch, dt=torch.int32), "idx": z(batch, 100, dt=torch.int32),
+                    "bbox": z(batch, 100, 4, dt=torch.float64), "dcls": z(batch, 100, dt=torch.int32),
+                    "score": z(batch, 100, dt=torch.float64)}
+        self.h_out = {k: torch.zeros_like(v, device="cpu").pin_memory() for k, v in self.out.items() if k in ("det", "cnt")}
+        self.layers = (m.ProposalLayer(context=self.ctx), m.PyramidROIAlignLayer({"poolSize": 7}, context=self.ctx),
+                       m.TimeDistributedClassifierLayer(context=self.ctx), m.DetectionLayer(context=self.ctx),
+                       m.PyramidROIAlignLayer({"poolSize": 14}, context=self.ctx))
+        self.h2d = sum(v.numel() * v.element_size() for v in self.h.values()) + sum(x.numel() * 4 for x in self.d_maps)
+        self.d2h = sum(v.numel() * v.element_size() for v in self.h_out.values())
+
+    def step(self, src=None, maps=None):
+        src = src or self.d
+        maps = maps or self.d_maps
+        o = self.out
+        prop, ra7, tdc, det, ra14 = self.layers
+        prop.evaluate([src["probs"], src["deltas"]], [o["rois"]])
+        ra7.evaluate([o["rois"]] + maps, [o["pooled"]])
+        tdc.select(src["cprob"], src["cbbox"], o["cls"])
+        det.evaluate([o["rois"], o["cls"]], [o["det"]])
+        ra14.evaluate([o["det"]] + maps, [o["pooled14"]])
+        self.m._cabi.check(self.ctx.handle, self.m.lib().mrcnn_detections_decode(
+            self.ctx.handle, self.b, o["det"].data_ptr(), None, o["cnt"].data_ptr(), o["idx"].data_ptr(),
+            o["bbox"].data_ptr(), o["dcls"].data_ptr(), o["score"].data_ptr(), None))
+
+    def step_e2e(self):
+        torch = self.torch
+        if self.h_maps is None:
+            self.h_maps = [x.cpu().pin_memory() for x in self.d_maps]
+            self.e_maps = [torch.empty_like(x) for x in self.d_maps]
+            self.e = {k: torch.empty_like(v) for k, v in self.d.items()}
+        for k, v in self.h.items():
+            self.e[k].copy_(v, non_blocking=True)
+        for a, b in zip(self.e_maps, self.h_maps):
+            a.copy_(b, non_blocking=True)
+        self.step(self.e, self.e_maps)
+        for k, v in self.h_out.items():
+            v.copy_(self.out[k], non_blocking=True)
+        self.stream.synchronize()
+
+    def launches_per_step(self):
+        c0 = self.ctx.launch_count
+        self.step()
+        return self.ctx.launch_count - c0
+
+    def roofline(self, prof, peaks):
+        ms, n, work = prof["roialign"]
+        ach = work / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        return {"kernel": "roialign_chw_kernel (pool 7 + pool 14 launches)", "bound": "hbm", "achieved": ach,
+                "peak": peaks["hbm"], "peak_source": peaks["source"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                "traffic": None, "launches": n, "avg_launch_ms": ms / max(n, 1),
+                "algorithmic_bytes_per_launch": work / max(n, 1)}
+
+
+class PipelineWorkload:
+    """BASELINE.json configs[1]: batch of 1024x1024x3 u8 images -> MaskRCNN.predict (ResNet101+FPN+RPN, ProposalLayer
+    6000 -> 1000, PyramidROIAlign, classifier head, DetectionLayer, mask head) through mrcnn_predict; with N > 1 ranks
+    every rank predicts its own batch and one NCCL all-gather collects all detections / masks (configs[3])."""
+    name = "pipeline"
+    dtype = "f16"     # tensor-core operands fp16 (as the reference stores its weights), fp32 accumulate; custom layers f32/f64
+
+    def __init__(self, m, torch, device, batch, rank, world, architecture=101):
+        self.m, self.torch, self.b, self.world = m, torch, batch, world
+        cfg = m.MaskRCNNConfig()
+        cfg.architecture = "resnet101" if architecture == 101 else "resnet50"
+        cfg.maxBatch = batch
+        _, blobs = m.weights.synthetic_blobs(architecture)
+        self.model = m.MaskRCNN(cfg, device=device, blobs=blobs, anchors=m.synth.generate_anchors(IMG, IMG))
+        self.ctx = self.model.ctx
+        self.stream = torch.cuda.Stream()
+        self.ctx.set_stream(self.stream.cuda_stream)
+        rng = np.random.default_rng(20260 + rank)
+        img = rng.integers(0, 256, (batch, IMG, IMG, 3), dtype=np.uint8)
+        self.h_img = torch.from_numpy(img).pin_memory()
+        self.d_img = self.h_img.cuda()
+        tot = batch * world
+        self.d_det = torch.zeros((tot, 100, 6), device="cuda")
+        self.d_mask = torch.zeros((tot, 100, 28, 28), device="cuda")
+        self.h_det = torch.zeros((tot, 100, 6)).pin_memory()
+        self.h_mask = torch.zeros((tot, 100, 28, 28)).pin_memory()
+        self.h2d = self.h_img.numel()
+        self.d2h = 4 * (self.h_det.numel() + self.h_mask.numel())
+        self.config_extra = {"model": "ResNet101+FPN Mask-RCNN, 81 classes, synthetic fp16 weights (seed 7)",
+                             "collective": "none" if world == 1 else "1 ncclAllGather of packed detections|masks per step"}
+        if world > 1:
+            import torch.distributed as dist
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                buf = (C.c_char * 128)()
+                m._cabi.check(None, m.lib().mrcnn_nccl_unique_id(buf))
+                uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+            uid = uid.cuda()
+            dist.broadcast(uid, 0)
+            raw = bytes(uid.cpu().numpy().tobytes())
+            m._cabi.check(self.ctx.handle, m.lib().mrcnn_comm_init(self.ctx.handle, raw, rank, world))
+
+    def _predict(self, img, det, mask):
+        l, h = self.m.lib(), self.ctx.handle
+        if self.world > 1:
+            self.m._cabi.check(h, l.mrcnn_predict_allgather(h, self.b, img.data_ptr(), det.data_ptr(), mask.data_ptr()))
+        else:
+            self.m._cabi.check(h, l.mrcnn_predict(h, self.b, img.data_ptr(), det.data_ptr(), mask.data_ptr()))
+
+    def step(self):
+        self._predict(self.d_img, self.d_det, self.d_mask)
+
+    def step_e2e(self):
+        # the reference-facing call with HOST buffers: H2D of the images and D2H of detections + masks happen inside
+        self._predict(self.h_img, self.h_det, self.h_mask)
+
+    def launches_per_step(self):
+        c0 = self.ctx.launch_count
+        self.step()
+        self.ctx.synchronize()
+        return self.ctx.launch_count - c0
+
+    def roofline(self, prof, peaks):
+        ms, n, work = prof["conv_gemm_tcgen05"]
+        ach = work / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        peak = peaks["bf16_sustained"]
+        return {"kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM convolution, every dense layer)", "bound": "tensor",
+                "achieved": ach, "peak": peak, "peak_source": peaks["source"] + " (sustained cuBLAS bf16; fp16 runs at the same rate)",
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "launches": n, "avg_launch_ms": ms / max(n, 1),
+                "algorithmic_flops_per_launch": work / max(n, 1)}
+
+    def extra_rooflines(self, prof, peaks):
+        ms, n, work = prof["roialign"]
+        ach = work / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        return {"roofline_roialign": {"kernel": "roialign_nhwc_kernel (pool 7 + pool 14)", "bound": "hbm", "achieved": ach,
+                                      "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None,
+                                      "launches": n, "avg_launch_ms": ms / max(n, 1)},
+                "stage_ms": dict(self.ctx.stage_times())}
+
+    def cpu_baseline(self):
+        from oracle import oracle as orc
+        import torch
+        orc.lib()
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cpu_pipeline_image(self.m, orc, 1000)                       # warm-up (weights to torch, page-in)
+        dt, stages = cpu_pipeline_image(self.m, orc, 0)
+        return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "1 image of the same workload after 1 warm-up image: PyTorch-CPU fp32 dense graphs (all host threads) "
+                          "+ oracle.c custom layers (1 thread)", "stage_seconds": stages}
+
+
+def make_workload(args, m, torch, device):
+    rank, world, _ = dist_env()
+    if args.workload == "pipeline":
+        return PipelineWorkload(m, torch, device, args.batch, rank, world)
+    return CustomLayersWorkload(m, torch, device, args.batch, 0)
+
+
+def run_ours(args):
+    import torch
+    rank, world, local = dist_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    import maskrcnn_b200 as m
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl = make_workload(args, m, torch, local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        # CUDA events on the stream the library launches on (wl.stream is the context's stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(wl.stream):
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    with torch.cuda.stream(wl.stream):
+        launches = wl.launches_per_step()
+        for _ in range(max(args.warmup, 3)):
+            wl.step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    wl.ctx.profile_enable(False)
+    total_ms = timed(wl.step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    # per-kernel-class timing pass (event pairs perturb the stream slightly -> separate from `value`)
+    wl.ctx.profile_enable(True)
+    barrier()
+    with torch.cuda.stream(wl.stream):
+        for _ in range(args.steps):
+            wl.step()
+    prof = wl.ctx.profile_read()
+    wl.ctx.profile_enable(False)
+    # end to end through host buffers
+    with torch.cuda.stream(wl.stream):
+        for _ in range(2):
+            wl.step_e2e()
+    e2e_ms = timed(wl.step_e2e, args.steps)
+
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    ms_step = total_ms / args.steps
+    imgs = args.batch * world
+    line = {
+        "metric": METRIC, "value": imgs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
+        "config": dict({"workload": wl.name, "image": "1024x1024x3", "batch_per_gpu": args.batch, "global_batch": imgs,
+                        "pre_nms": 6000, "rois": 1000, "detections": 100,
+                        "l2_policy": "per-step working set (batch activations + feature maps, > 1 GB) exceeds the 126 MB L2; no explicit flush"},
+                       **getattr(wl, "config_extra", {})),
+        "clocks": clocks,
+        "e2e": {"value": imgs / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": wl.h2d,
+                "d2h_bytes_per_step": wl.d2h},
+        "gpu_launches": launches * args.steps,
+        "roofline": wl.roofline(prof, peaks),
+        "kernel_classes": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps,
+                               "work_per_step": v[2] / args.steps} for k, v in prof.items() if v[1]},
+    }
+    if hasattr(wl, "extra_rooflines"):
+        line.update(wl.extra_rooflines(prof, peaks))
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = wl.cpu_baseline() if hasattr(wl, "cpu_baseline") else default_cpu_baseline(m)
+    print(json.dumps(line))
+
+
+def default_cpu_baseline(m):
+    from oracle import oracle as orc
+    orc.lib()
+    anchors = m.synth.generate_anchors(IMG, IMG)
+    maps = m.synth.feature_maps(0)
+    ts = [cpu_custom_layers_image(orc, m.synth, anchors, i, maps) for i in range(3)]
+    dt = float(np.mean(ts[1:]))
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "2 images (after 1 warm-up) of the same custom-layer workload, oracle/liboracle.so, single thread"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=[None, "pipeline", "custom_layers"])
+    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step (configs[1]: 8)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.workload is None:
+        args.workload = "pipeline"
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -243,6 +243,15 @@ MRCNN_API int mrcnn_predict_allgather(mrcnn_ctx* ctx, int batch_local, const uin
  * mrcnn_predict, names in names_out (static strings), returns count. */
 MRCNN_API int mrcnn_last_stage_times(const mrcnn_ctx* ctx, int max_stages,
                            const char** names_out, float* ms_out);
+/* Per-kernel-class device timing: while enabled, every kernel launch of this
+ * library is bracketed by a CUDA event pair on the context's stream.
+ * mrcnn_profile_read synchronises, then returns per class (static name) the summed
+ * milliseconds, the number of bracketed launches and their algorithmic work
+ * (bytes for the memory-bound classes, flops for conv_gemm_tcgen05) since the last
+ * read, and resets the accumulators.  Returns the number of classes written. */
+MRCNN_API int mrcnn_profile_enable(mrcnn_ctx* ctx, int on);
+MRCNN_API int mrcnn_profile_read(mrcnn_ctx* ctx, int max_classes, const char** names_out,
+                       float* ms_out, int64_t* launches_out, double* work_out);
 /* Number of kernels this library launched on ctx since creation. */
 MRCNN_API int64_t mrcnn_launch_count(const mrcnn_ctx* ctx);
 

@@ -126,6 +126,7 @@ void mrcnn_destroy(mrcnn_ctx* ctx) {
   cudaFree(ctx->d_fidx); cudaFree(ctx->d_fcount); cudaFree(ctx->d_dmask);
   cudaFree(ctx->d_roi_level);
   cudaFree(ctx->d_gather_send); cudaFree(ctx->d_gather_recv);
+  for (auto& pr : ctx->prof_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -165,12 +166,49 @@ int64_t mrcnn_launch_count(const mrcnn_ctx* ctx) { return ctx ? ctx->launches : 
 
 int mrcnn_last_stage_times(const mrcnn_ctx* ctx, int max_stages, const char** names_out, float* ms_out) {
   if (!ctx) return 0;
+  dense_collect_stage_times(const_cast<mrcnn_ctx*>(ctx));
   int n = 0;
   for (auto& kv : ctx->stage_ms) {
     if (n >= max_stages) break;
     if (names_out) names_out[n] = kv.first;
     if (ms_out) ms_out[n] = kv.second;
     ++n;
+  }
+  return n;
+}
+
+static const char* kProfNames[PROF_NUM_CLASSES] = {
+    "conv_gemm_tcgen05", "roialign", "topk_radix_select", "sort_decode", "nms_iou_mask", "nms_resolve",
+    "detection_filter", "detection_finalize", "glue"};
+
+int mrcnn_profile_enable(mrcnn_ctx* ctx, int on) {
+  if (!ctx) return MRCNN_EINVAL;
+  MRCNN_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->profiling = on != 0;
+  ctx->prof_recs.clear();
+  ctx->prof_used = 0;
+  return MRCNN_OK;
+}
+
+int mrcnn_profile_read(mrcnn_ctx* ctx, int max_classes, const char** names_out, float* ms_out,
+                       int64_t* launches_out, double* work_out) {
+  if (!ctx) return 0;
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return 0;
+  float ms[PROF_NUM_CLASSES] = {0};
+  int64_t cnt[PROF_NUM_CLASSES] = {0};
+  double work[PROF_NUM_CLASSES] = {0};
+  for (auto& r : ctx->prof_recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { ms[r.cls] += t; cnt[r.cls]++; work[r.cls] += r.work; }
+  }
+  ctx->prof_recs.clear();
+  ctx->prof_used = 0;
+  int n = PROF_NUM_CLASSES < max_classes ? PROF_NUM_CLASSES : max_classes;
+  for (int i = 0; i < n; ++i) {
+    if (names_out) names_out[i] = kProfNames[i];
+    if (ms_out) ms_out[i] = ms[i];
+    if (launches_out) launches_out[i] = cnt[i];
+    if (work_out) work_out[i] = work[i];
   }
   return n;
 }

@@ -67,6 +67,39 @@ struct mrcnn_ctx {
 
   // stage timing of last predict
   std::vector<std::pair<const char*, float>> stage_ms;
+
+  // ---- per-kernel-class device timing (mrcnn_profile_*) ----
+  bool profiling = false;
+  struct ProfRec { int cls; cudaEvent_t e0, e1; double work; };
+  std::vector<ProfRec> prof_recs;      // recorded since the last read
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pool;  // reusable event pairs
+  size_t prof_used = 0;
+};
+
+// Kernel classes reported by mrcnn_profile_read (names in api.cu, same order).
+enum ProfClass {
+  PROF_CONV_GEMM = 0, PROF_ROIALIGN, PROF_TOPK_SELECT, PROF_SORT_DECODE, PROF_NMS_MASK, PROF_NMS_RESOLVE,
+  PROF_DET_FILTER, PROF_DET_FINALIZE, PROF_GLUE, PROF_NUM_CLASSES
+};
+
+// RAII: brackets the launches issued in its scope with a CUDA event pair on the
+// context's stream when profiling is on (no-op otherwise).  `work` = algorithmic
+// bytes (memory-bound classes) or flops (PROF_CONV_GEMM) of those launches.
+struct ProfScope {
+  mrcnn_ctx* ctx; int idx = -1;
+  ProfScope(mrcnn_ctx* c, int cls, double work) : ctx(c) {
+    if (!c->profiling) return;
+    if (c->prof_used == c->prof_pool.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+      c->prof_pool.push_back({a, b});
+    }
+    auto& pr = c->prof_pool[c->prof_used++];
+    cudaEventRecord(pr.first, c->stream);
+    c->prof_recs.push_back({cls, pr.first, pr.second, work});
+    idx = (int)c->prof_recs.size() - 1;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(ctx->prof_recs[idx].e1, ctx->stream); }
 };
 
 inline int mrcnn_fail(mrcnn_ctx* ctx, int code, const std::string& msg);

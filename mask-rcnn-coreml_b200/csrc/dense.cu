@@ -28,6 +28,7 @@ static int launch_bn(mrcnn_ctx* ctx, const ConvPlan& plan) {
                                              cg::Cfg<BN>::kSmemBytes));
     attr_done = true;
   }
+  ProfScope ps(ctx, PROF_CONV_GEMM, plan.flops);
   conv_gemm_kernel<BN><<<plan.grid, CG_THREADS, cg::Cfg<BN>::kSmemBytes, ctx->stream>>>(plan.tmA, plan.tmB, plan.p);
   MRCNN_LAUNCH_CHECK(ctx);
   return MRCNN_OK;

@@ -43,3 +43,4 @@ int conv_plan_run(mrcnn_ctx* ctx, const ConvPlan& plan);
 int dense_load_weights(mrcnn_ctx* ctx, int which, const void* blob, size_t bytes);
 void dense_destroy(mrcnn_ctx* ctx);
 void comm_destroy(mrcnn_ctx* ctx);
+void dense_collect_stage_times(mrcnn_ctx* ctx);

@@ -152,6 +152,7 @@ int detection_run(mrcnn_ctx* ctx, int batch, int64_t R64, const float* d_rois, c
   const int words = ceil_div(R, 64);
   cudaStream_t s = ctx->stream;
   float4 sd = make_float4(cfg.bbox_std[0], cfg.bbox_std[1], cfg.bbox_std[2], cfg.bbox_std[3]);
+  ProfScope ps(ctx, PROF_DET_FILTER, (double)batch * R * (16 + 24 + 28));   // whole layer: filter + mask + finalize
   det_filter_kernel<<<batch, DET_THREADS, 0, s>>>((const float4*)d_rois, d_cls, R, sd, cfg.detection_min_score,
                                                    ctx->d_fbox, ctx->d_fcls, ctx->d_fscore, ctx->d_fidx, ctx->d_fcount);
   MRCNN_LAUNCH_CHECK(ctx);
@@ -206,6 +207,7 @@ int classifier_select_run(mrcnn_ctx* ctx, int batch, int64_t R, int ncls, const 
   int64_t total = (int64_t)batch * R;
   int threads = 256;
   int blocks = ceil_div(total * 32, threads);
+  ProfScope ps(ctx, PROF_GLUE, (double)total * (ncls * 4.0 + 16 + 24));
   classifier_select_kernel<<<blocks, threads, 0, ctx->stream>>>(d_probs, d_bbox, total, ncls, d_out);
   MRCNN_LAUNCH_CHECK(ctx);
   return MRCNN_OK;
@@ -267,6 +269,7 @@ __global__ void detections_decode_kernel(const float* __restrict__ det, const fl
 int detections_decode_run(mrcnn_ctx* ctx, int batch, int D, int S, const float* d_det, const float* d_masks,
                           int32_t* d_count, int32_t* d_index, double* d_bbox, int32_t* d_class,
                           double* d_score, uint8_t* d_mask_u8) {
+  ProfScope ps(ctx, PROF_GLUE, (double)batch * D * (24.0 + (d_masks ? 5.0 * S * S : 0.0) + 56.0));
   detections_decode_kernel<<<batch, 256, sizeof(int) * D, ctx->stream>>>(d_det, d_masks, D, S, d_count, d_index,
                                                                          d_bbox, d_class, d_score, d_mask_u8);
   MRCNN_LAUNCH_CHECK(ctx);

@@ -281,6 +281,8 @@ int proposal_run(mrcnn_ctx* ctx, int batch, int64_t N, const float* d_probs, con
   const int cand_stride = next_pow2(ctx->ws_pre);
   const int words = ceil_div(ctx->ws_pre, 64);
 
+  {
+  ProfScope ps(ctx, PROF_TOPK_SELECT, (double)batch * N * 8.0);
   sel_init_kernel<<<batch, 256, 0, s>>>(ctx->d_sel, ctx->d_hist, pre);
   MRCNN_LAUNCH_CHECK(ctx);
   dim3 grid(ceil_div(N, SEL_THREADS * SEL_ITEMS), batch);
@@ -297,6 +299,7 @@ int proposal_run(mrcnn_ctx* ctx, int batch, int64_t N, const float* d_probs, con
   sel_compact_kernel<<<grid, SEL_THREADS, 0, s>>>((const float2*)d_probs, N, idx_bits, ctx->d_sel,
                                                   ctx->d_cand, cand_stride);
   MRCNN_LAUNCH_CHECK(ctx);
+  }
   float4 sd = make_float4(cfg.bbox_std[0], cfg.bbox_std[1], cfg.bbox_std[2], cfg.bbox_std[3]);
 #define LAUNCH_SORT(SN)                                                                          \
   do {                                                                                           \
@@ -311,18 +314,25 @@ int proposal_run(mrcnn_ctx* ctx, int batch, int64_t N, const float* d_probs, con
         ctx->d_cand, cand_stride, pre, idx_bits, N, (const float4*)d_deltas,                     \
         (const float4*)ctx->d_anchors, sd, ctx->d_sboxes, ctx->d_sorder, stride);                \
   } while (0)
+  {
+  ProfScope ps(ctx, PROF_SORT_DECODE, (double)batch * pre * (8.0 + 32.0 + 20.0));
   if (sort_n <= 2048) LAUNCH_SORT(2048);
   else if (sort_n <= 4096) LAUNCH_SORT(4096);
   else if (sort_n <= 8192) LAUNCH_SORT(8192);
   else LAUNCH_SORT(16384);
 #undef LAUNCH_SORT
   MRCNN_LAUNCH_CHECK(ctx);
+  }
 
   const int tiles = ceil_div(pre, NMS_TILE);
   dim3 mgrid(tiles, tiles, batch);
+  {
+  ProfScope ps(ctx, PROF_NMS_MASK, (double)batch * pre * (16.0 + 8.0 * (words + 1) / 2));
   nms_mask_kernel<<<mgrid, NMS_TILE, 0, s>>>(ctx->d_sboxes, nullptr, nullptr, pre, stride, words,
                                              cfg.proposal_nms_iou, ctx->d_mask);
   MRCNN_LAUNCH_CHECK(ctx);
+  }
+  ProfScope ps2(ctx, PROF_NMS_RESOLVE, (double)batch * (cfg.max_proposals * 8.0 * words + cfg.max_proposals * 20.0));
   size_t rs = sizeof(unsigned long long) * (words + NMS_TILE) + sizeof(int) * (NMS_TILE + 4 + cfg.max_proposals);
   proposal_resolve_kernel<<<batch, 256, rs, s>>>(ctx->d_sboxes, ctx->d_sorder, ctx->d_mask, pre, stride,
                                                  words, cfg.max_proposals, (float4*)d_rois_out,

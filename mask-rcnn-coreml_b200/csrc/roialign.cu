@@ -168,6 +168,7 @@ static int roi_levels(mrcnn_ctx* ctx, int batch, const float* d_rois, int roi_st
   }
   // PyramidROIAlignLayer.swift:357 ratio = factor / sqrt(W*H)  (Q15: configured size always used)
   double ratio = (double)ctx->cfg.fpn_selection_factor / sqrt((double)ctx->cfg.image_w * (double)ctx->cfg.image_h);
+  ProfScope ps(ctx, PROF_GLUE, (double)total * (roi_stride * 4 + 4));
   roi_level_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(d_rois, roi_stride, total, ratio, ctx->d_roi_level);
   MRCNN_LAUNCH_CHECK(ctx);
   *d_level = ctx->d_roi_level;
@@ -190,6 +191,10 @@ int roialign_chw_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int roi_str
   }
   const int blk = (int)C * P * P;
   dim3 grid(ceil_div(blk, 1024), (unsigned)R, batch);
+  double map_bytes = 0;
+  for (int l = 0; l < 4; ++l) map_bytes += 4.0 * (double)C * pyr.h[l] * pyr.w[l];
+  // compulsory traffic: every level read once + output written once + rois
+  ProfScope ps(ctx, PROF_ROIALIGN, (double)batch * (map_bytes + 4.0 * R * blk + 4.0 * R * roi_stride));
   roialign_chw_kernel<<<grid, 256, 0, ctx->stream>>>(d_rois, roi_stride, (int)R, pyr, (int)C, P, lv, d_out);
   MRCNN_LAUNCH_CHECK(ctx);
   if (d_level_out)
@@ -209,6 +214,9 @@ int roialign_nhwc_f16_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int ro
   PyramidF16 pyr;
   for (int l = 0; l < 4; ++l) { pyr.p[l] = d_fmaps[l]; pyr.h[l] = hw[2 * l]; pyr.w[l] = hw[2 * l + 1]; }
   dim3 grid((unsigned)R, batch);
+  double map_bytes = 0;
+  for (int l = 0; l < 4; ++l) map_bytes += 2.0 * (double)C * pyr.h[l] * pyr.w[l];
+  ProfScope ps(ctx, PROF_ROIALIGN, (double)batch * (map_bytes + 2.0 * R * C * P * P + 4.0 * R * roi_stride));
   roialign_nhwc_kernel<<<grid, 256, 0, ctx->stream>>>(d_rois, roi_stride, (int)R, pyr, (int)C, P, lv, d_out);
   MRCNN_LAUNCH_CHECK(ctx);
   if (d_level_out)

@@ -80,6 +80,18 @@ class Context:
     def launch_count(self):
         return int(lib().mrcnn_launch_count(self.handle))
 
+    def profile_enable(self, on=True):
+        check(self.handle, lib().mrcnn_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_read(self):
+        """{kernel class: (ms, launches, algorithmic work)} since the last read (synchronises)."""
+        names = (C.c_char_p * 16)()
+        ms = (C.c_float * 16)()
+        cnt = (C.c_int64 * 16)()
+        work = (C.c_double * 16)()
+        n = lib().mrcnn_profile_read(self.handle, 16, names, ms, cnt, work)
+        return {names[i].decode(): (float(ms[i]), int(cnt[i]), float(work[i])) for i in range(n)}
+
     def stage_times(self):
         names = (C.c_char_p * 32)()
         ms = (C.c_float * 32)()

@@ -1,2 +1,141 @@
-"""placeholder (filled in with the dense model)"""
-Detection = MaskRCNN = MaskRCNNConfig = None
+"""The reference's public surface, host side: MaskRCNNConfig, Detection and the MaskRCNN model
+class (the Xcode-generated class over MaskRCNN.mlmodel: Example/Source/ViewController.swift:37),
+forwarding to mrcnn_predict / mrcnn_detections_decode of libmaskrcnn_cuda.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import check, lib, ptr
+from .layers import Context
+
+
+class MaskRCNNConfig:
+    """MaskRCNNConfig.swift:10-18: a global singleton with the artefact URLs.  The Swift class has only the
+    three URL properties; the layer parameters that Core ML bakes into the .mlmodel (ProposalLayer.swift:57-63,
+    DetectionLayer.swift:55-61, PyramidROIAlignLayer.swift:45-46) live here too, with the Swift defaults."""
+    defaultConfig = None
+
+    def __init__(self):
+        self.anchorsURL = None                    # MaskRCNNConfig.swift:15
+        self.compiledClassifierModelURL = None    # :16
+        self.compiledMaskModelURL = None          # :17
+        self.modelURL = None                      # the MaskRCNN model bundle itself (ViewController.swift:37)
+        self.architecture = "resnet101"           # README.md:87
+        self.imageShape = (1024, 1024, 3)         # README.md:88
+        self.numClasses = 81                      # README.md:89
+        self.preNMSMaxProposals = 6000            # ProposalLayer.swift:59
+        self.maxProposals = 1000                  # ProposalLayer.swift:61
+        self.maxDetections = 100                  # DetectionLayer.swift:57
+        self.maxBatch = 8
+
+    def context_overrides(self):
+        return dict(image_h=self.imageShape[0], image_w=self.imageShape[1],
+                    architecture={"resnet101": 101, "resnet50": 50}[self.architecture],
+                    num_classes=self.numClasses, pre_nms_max_proposals=self.preNMSMaxProposals,
+                    max_proposals=self.maxProposals, max_detections=self.maxDetections, max_batch=self.maxBatch,
+                    anchors_path=self.anchorsURL, main_model_path=self.modelURL,
+                    classifier_model_path=self.compiledClassifierModelURL, mask_model_path=self.compiledMaskModelURL)
+
+
+MaskRCNNConfig.defaultConfig = MaskRCNNConfig()
+
+
+class Detection:
+    """Detection.swift:15-21."""
+    __slots__ = ("index", "boundingBox", "classId", "score", "mask")
+
+    def __init__(self, index, boundingBox, classId, score, mask):
+        self.index, self.boundingBox, self.classId, self.score, self.mask = index, boundingBox, classId, score, mask
+
+    def __repr__(self):
+        return f"Detection(index={self.index}, classId={self.classId}, score={self.score:.4f}, boundingBox={self.boundingBox})"
+
+    @staticmethod
+    def detectionsFromFeatureValue(detections, mask=None, context=None):
+        """Detection.swift:23-62 (+ :64-99 for the 8-bit masks), computed on the device.
+        detections (D,6) / mask (D,S,S) for one image -> [Detection]."""
+        from .layers import default_context
+        ctx = context or default_context()
+        det = np.ascontiguousarray(detections, dtype=np.float32).reshape(1, -1, 6)
+        d = det.shape[1]
+        if d != ctx.cfg.max_detections:
+            raise _cabi.MaskRCNNError(_cabi.EINVAL, "detections must have max_detections rows")
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.float32)
+        s = 2 * ctx.cfg.pool_size_mask
+        cnt = np.zeros(1, np.int32); idx = np.zeros((1, d), np.int32); bbox = np.zeros((1, d, 4), np.float64)
+        cls = np.zeros((1, d), np.int32); score = np.zeros((1, d), np.float64)
+        mu8 = np.zeros((1, d, s * s), np.uint8) if m is not None else None
+        check(ctx.handle, lib().mrcnn_detections_decode(ctx.handle, 1, ptr(det), ptr(m), ptr(cnt), ptr(idx), ptr(bbox),
+                                                        ptr(cls), ptr(score), ptr(mu8)))
+        out = []
+        for i in range(int(cnt[0])):
+            out.append(Detection(int(idx[0, i]), tuple(bbox[0, i]), int(cls[0, i]), float(score[0, i]),
+                                 mu8[0, i].reshape(s, s).copy() if mu8 is not None else None))
+        return out
+
+
+class MaskRCNN:
+    """The model class: image (H,W,3) u8 -> outputs "detections" (100,6) and "mask" (100,28,28)
+    (I/O names Conversion/task.py:70-72).  `configuration` defaults to MaskRCNNConfig.defaultConfig,
+    like the custom layers of the reference read the singleton (ProposalLayer.swift:68)."""
+
+    def __init__(self, configuration=None, device=None, blobs=None, anchors=None):
+        cfg = configuration or MaskRCNNConfig.defaultConfig
+        self.config = cfg
+        ov = cfg.context_overrides()
+        if device is not None:
+            ov["device"] = device
+        self.ctx = Context(**ov)
+        if anchors is not None:
+            self.ctx.set_anchors(anchors)
+        if blobs is not None:                      # in-memory weights instead of files
+            for which, blob in enumerate(blobs):
+                self.ctx.set_weights(which, blob)
+        c = self.ctx.cfg
+        self.shape = (c.image_h, c.image_w, 3)
+        self.D, self.S = c.max_detections, 2 * c.pool_size_mask
+
+    def prediction_batch(self, images, detections=None, masks=None):
+        """images [B,H,W,3] u8 (numpy / torch, host or cuda) -> (detections [B,D,6], masks [B,D,S,S]) f32.
+        Output buffers may be passed in (same kinds); host outputs imply a stream synchronisation."""
+        b = images.shape[0]
+        if tuple(images.shape[1:]) != self.shape:
+            raise _cabi.MaskRCNNError(_cabi.EINVAL, f"images must be [B,{self.shape[0]},{self.shape[1]},3] uint8")
+        if detections is None:
+            detections = np.empty((b, self.D, 6), np.float32)
+        if masks is None:
+            masks = np.empty((b, self.D, self.S, self.S), np.float32)
+        check(self.ctx.handle, lib().mrcnn_predict(self.ctx.handle, b, ptr(images), ptr(detections), ptr(masks)))
+        return detections, masks
+
+    def prediction(self, image):
+        """One image -> {"detections": (D,6), "mask": (D,S,S)} like MaskRCNNOutput."""
+        d, m = self.prediction_batch(np.ascontiguousarray(image)[None])
+        return {"detections": d[0], "mask": m[0]}
+
+    def predict(self, image):
+        """image -> [Detection] (score > 0.7), the call pattern of ViewController.swift:163-187."""
+        out = self.prediction(image)
+        return Detection.detectionsFromFeatureValue(out["detections"], out["mask"], context=self.ctx)
+
+    def close(self):
+        self.ctx.close()
+
+
+def smoke_predict():
+    """Tiny end-to-end MaskRCNN.predict (ResNet50, 256x256) used by __graft_entry__.smoke()."""
+    from . import synth, weights
+    cfg = MaskRCNNConfig()
+    cfg.architecture, cfg.imageShape, cfg.preNMSMaxProposals, cfg.maxProposals, cfg.maxBatch = "resnet50", (256, 256, 3), 1000, 200, 2
+    _, blobs = weights.synthetic_blobs(50)
+    model = MaskRCNN(cfg, blobs=blobs, anchors=synth.generate_anchors(256, 256))
+    rng = np.random.default_rng(20260)
+    img = rng.integers(0, 256, (256, 256, 3), dtype=np.uint8)
+    out = model.prediction(img)
+    dets = Detection.detectionsFromFeatureValue(out["detections"], out["mask"], context=model.ctx)
+    assert np.isfinite(out["detections"]).all() and np.isfinite(out["mask"]).all()
+    print(f"smoke: MaskRCNN.predict ok, {len(dets)} detections, stages:",
+          ", ".join(f"{n} {ms:.2f} ms" for n, ms in model.ctx.stage_times()))
+    model.close()

@@ -1,0 +1,167 @@
+"""GPU tests of the dense graphs and the fused pipeline.
+
+Dense stages (tensor-core fp16, fp32 accumulate) are compared with a plain PyTorch fp32 reference of the
+same ops on the same inputs (oracle/dense_ref.py) within a stated tolerance; the fused mrcnn_predict is then
+required to be BIT-IDENTICAL to the stage-wise chain  backbone_eval -> oracle ProposalLayer -> oracle
+PyramidROIAlign -> classifier_eval -> oracle DetectionLayer -> oracle PyramidROIAlign -> mask_eval,
+i.e. every custom layer inside the pipeline matches the oracle on the pipeline's own intermediate tensors."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SIZE = 256
+
+
+@pytest.fixture(scope="module")
+def small(pkg):
+    """ResNet50 / 256x256 / 200 proposals model with seeded synthetic weights."""
+    import torch
+    assert torch.cuda.is_available()
+    folded, blobs = pkg.weights.synthetic_blobs(50)
+    cfg = pkg.MaskRCNNConfig()
+    cfg.architecture, cfg.imageShape, cfg.preNMSMaxProposals, cfg.maxProposals, cfg.maxBatch = "resnet50", (SIZE, SIZE, 3), 1000, 200, 2
+    anchors = pkg.synth.generate_anchors(SIZE, SIZE)
+    model = pkg.MaskRCNN(cfg, blobs=blobs, anchors=anchors)
+    rng = np.random.default_rng(20260)
+    # smooth-ish images so that feature maps are not pure noise
+    img = rng.integers(0, 256, (2, SIZE // 8, SIZE // 8, 3)).astype(np.uint8).repeat(8, 1).repeat(8, 2)
+    img = (img.astype(np.int32) + rng.integers(-20, 20, img.shape)).clip(0, 255).astype(np.uint8)
+    yield {"model": model, "folded": folded, "anchors": anchors, "img": img}
+    model.close()
+
+
+def _backbone(pkg, model, img):
+    import torch
+    b = img.shape[0]
+    c = model.ctx.cfg
+    sizes = [(c.image_h // s, c.image_w // s) for s in (4, 8, 16, 32)]
+    fm = [torch.zeros((b, h, w, 256), dtype=torch.float16, device="cuda") for h, w in sizes]
+    n = int(sum(3 * (c.image_h // s) * (c.image_w // s) for s in (4, 8, 16, 32, 64)))
+    probs = torch.zeros((b, n, 2), device="cuda"); deltas = torch.zeros((b, n, 4), device="cuda")
+    fp = (C.c_void_p * 4)(*[t.data_ptr() for t in fm])
+    pkg._cabi.check(model.ctx.handle, pkg.lib().mrcnn_backbone_eval(model.ctx.handle, b, pkg._cabi.ptr(img), fp, probs.data_ptr(),
+                                                                 deltas.data_ptr()))
+    return [t.cpu().numpy() for t in fm], probs.cpu().numpy(), deltas.cpu().numpy()
+
+
+def _relerr(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    return np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-6), np.abs(got - ref).mean() / max(np.abs(ref).mean(), 1e-6)
+
+
+def test_backbone_fpn_rpn_vs_torch(pkg, small):
+    from oracle.dense_ref import Ref
+    fm, probs, deltas = _backbone(pkg, small["model"], small["img"])
+    ref = Ref(small["folded"], 50)
+    rfm, rprobs, rdeltas = ref.backbone(small["img"])
+    assert probs.shape[1] == small["anchors"].shape[0]
+    for l in range(4):
+        mx, mean = _relerr(fm[l].astype(np.float32), rfm[l].cpu().numpy())
+        assert mx < 3e-2 and mean < 3e-3, (l, mx, mean)          # fp16 activations: tolerance relative to the map's scale
+    assert np.abs(probs - rprobs.cpu().numpy()).max() < 2e-2
+    mx, mean = _relerr(deltas, rdeltas.cpu().numpy())
+    assert mx < 3e-2 and mean < 3e-3, (mx, mean)
+    assert probs.std() > 0.05                                    # the synthetic RPN is not degenerate
+
+
+def test_classifier_head_vs_torch(pkg, small):
+    from oracle.dense_ref import Ref
+    m = small["model"]
+    rng = np.random.default_rng(5)
+    pooled = rng.standard_normal((1, 200, 256, 7, 7)).astype(np.float16).astype(np.float32)
+    out = np.zeros((1, 200, 6), np.float32)
+    pkg.TimeDistributedClassifierLayer(context=m.ctx).evaluate([pooled], [out])
+    probs, bbox, _ = Ref(small["folded"], 50).classifier(pooled[0].transpose(0, 2, 3, 1))
+    probs, bbox = probs.cpu().numpy(), bbox.cpu().numpy().reshape(200, 81, 4)
+    cls = out[0, :, 4].astype(int)
+    # class ids: identical wherever the reference's top-2 margin exceeds the numeric tolerance
+    srt = np.sort(probs, axis=1)
+    clear = (srt[:, -1] - srt[:, -2]) > 2e-2
+    assert clear.sum() > 100
+    np.testing.assert_array_equal(cls[clear], probs.argmax(1)[clear])
+    np.testing.assert_allclose(out[0, :, 5], probs[np.arange(200), cls], atol=2e-2)
+    np.testing.assert_allclose(out[0, :, :4], bbox[np.arange(200), cls], atol=3e-2 * np.abs(bbox).max())
+
+
+def test_mask_head_vs_torch(pkg, small):
+    from oracle.dense_ref import Ref
+    m = small["model"]
+    rng = np.random.default_rng(6)
+    d = 100
+    pooled = rng.standard_normal((1, d, 256, 14, 14)).astype(np.float16).astype(np.float32)
+    pooled[0, 60:] = 0.0                                          # padding blocks (removeZeros)
+    det = np.zeros((1, d, 6), np.float32)
+    det[0, :60, 4] = rng.integers(1, 81, 60)
+    det[0, :60, 5] = 0.9
+    out = np.full((1, d, 28, 28), 7.0, np.float32)
+    pkg.TimeDistributedMaskLayer(context=m.ctx).evaluate([pooled, det], [out])
+    ref = Ref(small["folded"], 50).mask(pooled[0, :60].transpose(0, 2, 3, 1)).cpu().numpy()
+    want = ref[np.arange(60), det[0, :60, 4].astype(int)]
+    np.testing.assert_allclose(out[0, :60], want, atol=1e-2)
+    assert not out[0, 60:].any()                                  # TimeDistributedMaskLayer.swift:87-89
+    assert 0.05 < out[0, :60].std()
+
+
+def test_predict_equals_stagewise_chain_with_oracle_layers(pkg, small, orc):
+    import torch
+    m, img, anchors = small["model"], small["img"], small["anchors"]
+    b = img.shape[0]
+    det, masks = m.prediction_batch(img)
+    stages = dict(m.ctx.stage_times())
+    assert "Proposal-Eval" in stages and "TimeDistributedMask-Eval" in stages
+    fm, probs, deltas = _backbone(pkg, m, img)
+    for i in range(b):
+        rois, _, cnt = orc.proposal(probs[i], deltas[i], anchors, pre_nms=1000, max_proposals=200)
+        pooled, _ = orc.pyramid_roialign_nhwc_f16(rois, [f[i] for f in fm], 7, SIZE, SIZE)
+        cls6 = np.zeros((1, 200, 6), np.float32)
+        pkg.TimeDistributedClassifierLayer(context=m.ctx).evaluate(
+            [np.ascontiguousarray(pooled.astype(np.float32).transpose(0, 3, 1, 2))[None]], [cls6])
+        d0, _, n0 = orc.detection(rois, cls6[0])
+        np.testing.assert_array_equal(det[i], d0)                 # bit-exact class ids / boxes / scores
+        pooled14, lv = orc.pyramid_roialign_nhwc_f16(d0, [f[i] for f in fm], 14, SIZE, SIZE)
+        mk = np.zeros((1, 100, 28, 28), np.float32)
+        pkg.TimeDistributedMaskLayer(context=m.ctx).evaluate(
+            [np.ascontiguousarray(pooled14.astype(np.float32).transpose(0, 3, 1, 2))[None], d0[None]], [mk])
+        np.testing.assert_array_equal(masks[i], mk[0])
+        assert n0 == (d0[:, 5] > 0).sum()
+    assert (det[..., 5] > 0).sum() > 0, "synthetic weights should produce some detections"
+
+
+def test_predict_properties_and_device_buffers(pkg, small):
+    import torch
+    m, img = small["model"], small["img"]
+    d_img = torch.from_numpy(img).cuda()
+    d_det = torch.full((2, 100, 6), 9.0, device="cuda"); d_mask = torch.full((2, 100, 28, 28), 9.0, device="cuda")
+    m.prediction_batch(d_img, d_det, d_mask)
+    m.ctx.synchronize()
+    det, masks = m.prediction_batch(img)
+    np.testing.assert_array_equal(d_det.cpu().numpy(), det)       # host and device entry are the same computation
+    np.testing.assert_array_equal(d_mask.cpu().numpy(), masks)
+    for i in range(2):
+        n = int((det[i, :, 5] > 0).sum())
+        assert (det[i, n:] == 0).all() and (masks[i, n:] == 0).all()
+        s = det[i, :n, 5]
+        assert (np.diff(s) <= 0).all() and (s >= np.float32(0.7)).all()
+        assert ((det[i, :n, 4] >= 1) & (det[i, :n, 4] <= 80)).all()
+        assert (det[i, :n, :4] >= 0).all() and (det[i, :n, :4] <= 1).all()
+        assert ((masks[i, :n] > 0) & (masks[i, :n] < 1)).all()
+    dets = m.predict(img[0])
+    assert all(dd.score > 0.7 and dd.mask.shape == (28, 28) and dd.mask.dtype == np.uint8 for dd in dets)
+    # batch of 1 == first image of the batch of 2
+    det1, masks1 = m.prediction_batch(img[:1])
+    np.testing.assert_array_equal(det1[0], det[0])
+    np.testing.assert_array_equal(masks1[0], masks[0])
+
+
+def test_missing_weights_fail_loudly(pkg):
+    c = pkg.Context(image_h=SIZE, image_w=SIZE, max_batch=1)
+    img = np.zeros((1, SIZE, SIZE, 3), np.uint8)
+    with pytest.raises(pkg.MaskRCNNError):
+        pkg._cabi.check(c.handle, pkg.lib().mrcnn_predict(c.handle, 1, pkg._cabi.ptr(img), pkg._cabi.ptr(np.zeros((1, 100, 6), np.float32)),
+                                                        pkg._cabi.ptr(np.zeros((1, 100, 28, 28), np.float32))))
+    with pytest.raises(pkg.MaskRCNNError):
+        c.set_weights(0, b"garbage-not-a-blob-------------------")
+    c.close()
