@@ -47,6 +47,8 @@ struct ConvGemmParams {
   int res_h, res_w, res_ld;
   int deconv;                  // 1: cout = 4*deconv_c, output pixel (2y+dy, 2x+dx), channel c (2x2 stride-2 transposed conv)
   int deconv_c;
+  int tma_out;                 // 1: fp16 NHWC output staged in smem and written with TMA stores (cout % 64 == 0)
+  int tma_res;                 // 1: residual (res_mode 1) tiles fetched with TMA into the same staging buffers
   const float* bias;           // [cout] or nullptr
   const __half* residual;
   void* out;
@@ -91,6 +93,28 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+      ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N> __device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -154,7 +178,9 @@ template <int BN> struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN >= 256) ? 4 : ((BN >= 128) ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // BN in {32,64,128,256} -> power of two
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kOutStageBytes = CG_BM * 64 * 2;           // one 128-pixel x 64-channel fp16 sub-tile (SWIZZLE_128B)
+  static constexpr int kOutBytes = 2 * kOutStageBytes;            // double buffered
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 }  // namespace cg
@@ -162,20 +188,23 @@ template <int BN> struct Cfg {
 template <int BN>
 __global__ void __launch_bounds__(CG_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                  const __grid_constant__ ConvGemmParams p) {
   using C = cg::Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-B aligned operand ring (SWIZZLE_128B requirement)
   const uint32_t smem_base = (cg::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
-  // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base slot
+  const uint32_t out_base = smem_base + C::kStages * C::kStageBytes;     // 2 x 16 KB output / residual staging
+  const uint32_t bar_base = out_base + C::kOutBytes;
+  // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; the TMEM base slot; res_full[2]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4);
+  auto rfull_bar = [&](int b) { return bar_base + 8u * (2 * C::kStages + 5 + b); };
   uint8_t* smem_gen = smem_raw + (smem_base - cg::smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + C::kStages * C::kStageBytes + 8 * (2 * C::kStages + 4));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + C::kStages * C::kStageBytes + C::kOutBytes + 8 * (2 * C::kStages + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -184,7 +213,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     cg::prefetch_tmap(&tmA);
     cg::prefetch_tmap(&tmB);
     for (int s = 0; s < C::kStages; ++s) { cg::mbar_init(full_bar(s), 1); cg::mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { cg::mbar_init(tfull_bar(a), 1); cg::mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { cg::mbar_init(tfull_bar(a), 1); cg::mbar_init(tempty_bar(a), 4); cg::mbar_init(rfull_bar(a), 1); }
     cg::fence_barrier_init();
   }
   if (warp == 1) cg::tmem_alloc(tmem_slot, C::kTmemCols);
@@ -257,6 +286,121 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;          // accumulator row = pixel inside the tile
     int acc = 0; uint32_t acc_phase = 0;
+    if (p.tma_out) {
+      // ---- staged epilogue: TMEM -> regs -> (+bias, +residual, ReLU) -> fp16 -> swizzled smem -> TMA store.
+      // The residual sub-tile (same geometry as the output sub-tile) is TMA-loaded into the very staging
+      // buffer the result is then written to, one 64-channel chunk ahead of its use.
+      const bool e0 = (threadIdx.x == 64);   // warp 2, lane 0: issues all bulk copies of this CTA's epilogue
+      const int nchunks = (min(BN, p.cout) + 63) / 64;
+      auto tile_coords = [&](int tile, int& n0, int& x0, int& y0, int& img) {
+        const int nt = tile % p.tiles_n;
+        const int mt = tile / p.tiles_n;
+        n0 = nt * BN;
+        x0 = (mt % p.tiles_x) * p.tw;
+        y0 = ((mt / p.tiles_x) % p.tiles_y) * p.th;
+        img = mt / (p.tiles_x * p.tiles_y);
+      };
+      uint32_t cc = 0;                       // chunk counter of this CTA (buffer = cc & 1)
+      if (p.tma_res && e0 && (int)blockIdx.x < total_tiles) {
+        cg::prefetch_tmap(&tmC); cg::prefetch_tmap(&tmR);
+        int n0, x0, y0, img;
+        tile_coords(blockIdx.x, n0, x0, y0, img);
+        cg::mbar_expect_tx(rfull_bar(0), (uint32_t)C::kOutStageBytes);
+        cg::tma_load_4d(out_base, &tmR, rfull_bar(0), n0, x0, y0, img);
+      }
+      const uint32_t row_off = (uint32_t)row * 128u;
+      const uint32_t sw = (uint32_t)(row & 7);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int n0, x0, y0, img;
+        tile_coords(tile, n0, x0, y0, img);
+        const int x = x0 + (row % p.tw), y = y0 + (row / p.tw);
+        const bool pix_ok = (x < p.w_out) && (y < p.h_out);
+        const __half* res_row = nullptr;
+        if (p.res_mode == 2 && pix_ok)       // FPN top-down: nearest 2x up-sampled residual, gathered directly
+          res_row = p.residual + (((size_t)img * p.res_h + (y >> 1)) * (size_t)p.res_w + (x >> 1)) * (size_t)p.res_ld;
+        cg::mbar_wait(tfull_bar(acc), acc_phase);
+        cg::tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+        #pragma unroll 1
+        for (int c = 0; c < nchunks; ++c, ++cc) {
+          const uint32_t buf = cc & 1u;
+          const uint32_t sbuf = out_base + buf * (uint32_t)C::kOutStageBytes;
+          const int nc = n0 + c * 64;
+          if (p.tma_res) {
+            cg::mbar_wait(rfull_bar(buf), (cc >> 1) & 1u);      // residual chunk has landed (also: buffer is free)
+          } else {
+            cg::epi_bar_sync();                                  // e0 has seen the store that last read this buffer finish
+          }
+          #pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t v[32];
+            cg::tmem_ld32(t_addr + (uint32_t)(c * 64 + hh * 32), v);
+            cg::tmem_ld_wait();
+            #pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int n = nc + hh * 32 + g * 8;
+              const uint32_t saddr = sbuf + row_off + ((((uint32_t)(hh * 4 + g)) ^ sw) << 4);
+              float f[8];
+              #pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
+              if (p.bias && n < p.cout) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + 1);
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              if (p.tma_res) {
+                const uint4 rv = cg::lds128(saddr);
+                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+                #pragma unroll
+                for (int e = 0; e < 4; ++e) { float2 r2 = __half22float2(rh[e]); f[2 * e] += r2.x; f[2 * e + 1] += r2.y; }
+              } else if (res_row) {
+                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_row + n));
+                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+                #pragma unroll
+                for (int e = 0; e < 4; ++e) { float2 r2 = __half22float2(rh[e]); f[2 * e] += r2.x; f[2 * e + 1] += r2.y; }
+              }
+              if (p.relu) {
+                #pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
+              }
+              uint4 ov;
+              __half2* oh = reinterpret_cast<__half2*>(&ov);
+              #pragma unroll
+              for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+              cg::sts128(saddr, ov);
+            }
+          }
+          if (c == nchunks - 1) {            // accumulator fully read: hand the TMEM stage back to the MMA warp
+            cg::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) cg::mbar_arrive(tempty_bar(acc));
+          }
+          cg::fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the bulk-copy engine
+          cg::epi_bar_sync();
+          if (e0) {
+            cg::tma_store_4d(&tmC, sbuf, nc, x0, y0, img);
+            cg::bulk_commit();
+            cg::bulk_wait_read<1>();         // the store that used the OTHER buffer has finished reading it
+            if (p.tma_res) {                 // fetch the next chunk's residual into that buffer
+              int nn0 = n0, nx0 = x0, ny0 = y0, nimg = img, ncol = nc + 64;
+              bool have = true;
+              if (c == nchunks - 1) {
+                const int nt = tile + gridDim.x;
+                have = nt < total_tiles;
+                if (have) { tile_coords(nt, nn0, nx0, ny0, nimg); ncol = nn0; }
+              }
+              if (have) {
+                cg::mbar_expect_tx(rfull_bar(buf ^ 1u), (uint32_t)C::kOutStageBytes);
+                cg::tma_load_4d(out_base + (buf ^ 1u) * (uint32_t)C::kOutStageBytes, &tmR, rfull_bar(buf ^ 1u), ncol, nx0, ny0, nimg);
+              }
+            }
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+      if (e0) cg::bulk_wait<0>();
+    } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % p.tiles_n;
       const int mt = tile / p.tiles_n;

@@ -29,7 +29,7 @@ static int launch_bn(mrcnn_ctx* ctx, const ConvPlan& plan) {
     attr_done = true;
   }
   ProfScope ps(ctx, PROF_CONV_GEMM, plan.flops);
-  conv_gemm_kernel<BN><<<plan.grid, CG_THREADS, cg::Cfg<BN>::kSmemBytes, ctx->stream>>>(plan.tmA, plan.tmB, plan.p);
+  conv_gemm_kernel<BN><<<plan.grid, CG_THREADS, cg::Cfg<BN>::kSmemBytes, ctx->stream>>>(plan.tmA, plan.tmB, plan.tmC, plan.tmR, plan.p);
   MRCNN_LAUNCH_CHECK(ctx);
   return MRCNN_OK;
 }
@@ -131,6 +131,26 @@ int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan) {
     char b[128];
     snprintf(b, sizeof(b), "conv: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
     return mrcnn_fail(ctx, MRCNN_ECUDA, b);
+  }
+  // ---- C (and residual R): 4-D (C, W, H, N) views of the NHWC fp16 output, box (64, tw, th, 1)
+  plan->tmC = plan->tmB; plan->tmR = plan->tmB;      // valid placeholders when the staged epilogue is off
+  p.tma_out = (!L.no_tma_epilogue && !L.out_f32 && !L.deconv && (L.cout % 64) == 0 && bn >= 64) ? 1 : 0;
+  p.tma_res = (p.tma_out && p.res_mode == 1) ? 1 : 0;
+  if (p.tma_out) {
+    cuuint64_t cdims[4] = {(cuuint64_t)L.cout, (cuuint64_t)p.w_out, (cuuint64_t)p.h_out, (cuuint64_t)L.n};
+    cuuint64_t cstr[3] = {(cuuint64_t)p.ldc * 2, (cuuint64_t)p.ldc * 2 * p.w_out, (cuuint64_t)p.ldc * 2 * p.w_out * p.h_out};
+    cuuint32_t cbox[4] = {64, (cuuint32_t)p.tw, (cuuint32_t)p.th, 1};
+    cuuint32_t ces[4] = {1, 1, 1, 1};
+    r = enc(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, L.out, cdims, cstr, cbox, ces, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return mrcnn_fail(ctx, MRCNN_ECUDA, "conv: cuTensorMapEncodeTiled(C) failed");
+    if (p.tma_res) {
+      MRCNN_REQUIRE(ctx, p.res_h == p.h_out && p.res_w == p.w_out, "conv: residual shape must equal the output shape");
+      cuuint64_t rstr[3] = {(cuuint64_t)p.res_ld * 2, (cuuint64_t)p.res_ld * 2 * p.w_out, (cuuint64_t)p.res_ld * 2 * p.w_out * p.h_out};
+      r = enc(&plan->tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)L.residual, cdims, rstr, cbox, ces, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return mrcnn_fail(ctx, MRCNN_ECUDA, "conv: cuTensorMapEncodeTiled(R) failed");
+    }
   }
   return MRCNN_OK;
 }

@@ -27,10 +27,11 @@ struct ConvLaunch {
   int h_out = 0, w_out = 0;      // 0 -> derived from kh/kw/stride/pad
   int ldc = 0;                   // 0 -> round_up(cout, 8)
   int tw = 0, th = 0, bn = 0;    // 0 -> auto
+  int no_tma_epilogue = 0;       // force the direct-store epilogue (tests)
 };
 
 struct ConvPlan {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC, tmR;
   ConvGemmParams p;
   int bn = 0, grid = 0;
   size_t smem = 0;

@@ -27,6 +27,13 @@ CASES = [
     (1, 8, 8, 64, 24, 1, 1, 0, False, False),          # tiny map, cout not a multiple of 32
     (1, 64, 64, 64, 128, 3, 1, 1, False, True),
     (1, 1, 300, 1024, 408, 1, 1, 0, False, False),     # GEMM-like (FC layers): h = 1
+    # staged (TMA store) epilogue: many tiles per CTA, 1..4 chunks of 64 channels, TMA-prefetched residual
+    (8, 64, 64, 64, 256, 1, 1, 0, True, True),
+    (4, 40, 56, 128, 512, 1, 1, 0, True, True),        # two N tiles x four chunks, partial tiles
+    (2, 30, 30, 256, 128, 3, 1, 1, True, False),       # BN = 128, ragged edges
+    (3, 64, 64, 256, 512, 1, 2, 0, False, True),       # stride 2 (first 1x1 of a stage)
+    (2, 14, 14, 64, 64, 3, 1, 1, True, True),          # single chunk with residual
+    (1, 1, 1000, 12544, 1024, 1, 1, 0, False, True),   # classifier-head GEMM (long K)
 ]
 
 
