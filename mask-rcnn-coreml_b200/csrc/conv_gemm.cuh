@@ -180,8 +180,136 @@ template <int BN> struct Cfg {
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // BN in {32,64,128,256} -> power of two
   static constexpr int kOutStageBytes = CG_BM * 64 * 2;           // one 128-pixel x 64-channel fp16 sub-tile (SWIZZLE_128B)
   static constexpr int kOutBytes = 2 * kOutStageBytes;            // double buffered
-  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias tile*/;
 };
+
+// ---- staged epilogue (fp16 NHWC outputs): TMEM -> regs -> (+bias, +residual, ReLU) -> fp16 -> swizzled smem ->
+// TMA store, one 64-channel chunk at a time through two 16 KB staging buffers.  RES = 0: no residual;
+// 1: the residual sub-tile (same geometry as the output sub-tile) is TMA-loaded one chunk ahead into the very
+// buffer the result is then written to; 2: FPN top-down add, residual gathered from the half-resolution map.
+// Branch-free inner loop: flags are compile-time (RES) or folded into data (bias tile in smem, ReLU floor).
+template <int BN, int RES>
+__device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, const CUtensorMap* tmC, const CUtensorMap* tmR,
+                                                uint8_t* out_gen, uint32_t out_base, float* bias_gen,
+                                                uint32_t rfull0, uint32_t tfull0, uint32_t tempty0,
+                                                uint32_t tmem_base, int total_tiles, int warp, int lane) {
+  constexpr int kStageBytes = CG_BM * 64 * 2;
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+  const bool e0 = (threadIdx.x == 64);     // warp 2, lane 0: issues all bulk copies of this CTA's epilogue
+  const int nchunks = (min(BN, p.cout) + 63) / 64;
+  const float lo = p.relu ? 0.0f : -INFINITY;
+  auto tile_coords = [&](int tile, int& n0, int& x0, int& y0, int& img) {
+    const int nt = tile % p.tiles_n;
+    const int mt = tile / p.tiles_n;
+    n0 = nt * BN;
+    x0 = (mt % p.tiles_x) * p.tw;
+    y0 = ((mt / p.tiles_x) % p.tiles_y) * p.th;
+    img = mt / (p.tiles_x * p.tiles_y);
+  };
+  uint32_t cc = 0;                         // chunk counter of this CTA (buffer = cc & 1)
+  int bias_n0 = -1;
+  int acc = 0; uint32_t acc_phase = 0;
+  if (e0) { prefetch_tmap(tmC); if (RES == 1) prefetch_tmap(tmR); }
+  if (RES == 1 && e0 && (int)blockIdx.x < total_tiles) {
+    int n0, x0, y0, img;
+    tile_coords(blockIdx.x, n0, x0, y0, img);
+    mbar_expect_tx(rfull0, (uint32_t)kStageBytes);
+    tma_load_4d(out_base, tmR, rfull0, n0, x0, y0, img);
+  }
+  const uint32_t row_off = (uint32_t)row * 128u;
+  const uint32_t sw = (uint32_t)(row & 7);
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int n0, x0, y0, img;
+    tile_coords(tile, n0, x0, y0, img);
+    const __half* res_row = p.residual;    // RES == 2: always a readable address (rows outside the map are clipped by the store)
+    if (RES == 2) {
+      int x = x0 + (row % p.tw), y = y0 + (row / p.tw);
+      x = min(x, p.w_out - 1); y = min(y, p.h_out - 1);
+      res_row = p.residual + (((size_t)img * p.res_h + (y >> 1)) * (size_t)p.res_w + (x >> 1)) * (size_t)p.res_ld;
+    }
+    if (n0 != bias_n0) {                   // stage this N tile's bias (zeros when there is none) in smem
+      epi_bar_sync();
+      for (int i = threadIdx.x - 64; i < BN; i += 128)
+        bias_gen[i] = (p.bias && n0 + i < p.cout) ? __ldg(p.bias + n0 + i) : 0.0f;
+      bias_n0 = n0;
+      epi_bar_sync();
+    }
+    mbar_wait(tfull0 + 8u * acc, acc_phase);
+    tc_fence_after();
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+    #pragma unroll 1
+    for (int c = 0; c < nchunks; ++c, ++cc) {
+      const uint32_t buf = cc & 1u;
+      uint8_t* srow = out_gen + buf * kStageBytes + row_off;
+      const int nc = n0 + c * 64;
+      if (RES == 1) mbar_wait(rfull0 + 8u * buf, (cc >> 1) & 1u);   // residual chunk has landed (so the buffer is free, too)
+      else epi_bar_sync();                                            // e0 has seen the store that last read this buffer finish
+      #pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[32];
+        tmem_ld32(t_addr + (uint32_t)(c * 64 + hh * 32), v);
+        // operands that do not depend on the accumulator are fetched while the TMEM load is in flight
+        float4 bq[8];
+        uint4 rq[4];
+        #pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4* bp = reinterpret_cast<const float4*>(bias_gen + (c * 64 + hh * 32 + g * 8));
+          bq[2 * g] = bp[0]; bq[2 * g + 1] = bp[1];
+          if (RES == 1) rq[g] = *reinterpret_cast<const uint4*>(srow + ((((uint32_t)(hh * 4 + g)) ^ sw) << 4));
+          if (RES == 2) rq[g] = __ldg(reinterpret_cast<const uint4*>(res_row + nc + hh * 32 + g * 8));
+        }
+        tmem_ld_wait();
+        #pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+          #pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
+          f[0] += bq[2 * g].x; f[1] += bq[2 * g].y; f[2] += bq[2 * g].z; f[3] += bq[2 * g].w;
+          f[4] += bq[2 * g + 1].x; f[5] += bq[2 * g + 1].y; f[6] += bq[2 * g + 1].z; f[7] += bq[2 * g + 1].w;
+          if (RES != 0) {
+            const __half2* rh = reinterpret_cast<const __half2*>(&rq[g]);
+            #pragma unroll
+            for (int e = 0; e < 4; ++e) { const float2 r2 = __half22float2(rh[e]); f[2 * e] += r2.x; f[2 * e + 1] += r2.y; }
+          }
+          uint4 ov;
+          __half2* oh = reinterpret_cast<__half2*>(&ov);
+          #pragma unroll
+          for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(fmaxf(f[2 * e], lo), fmaxf(f[2 * e + 1], lo));
+          *reinterpret_cast<uint4*>(srow + ((((uint32_t)(hh * 4 + g)) ^ sw) << 4)) = ov;
+        }
+      }
+      if (c == nchunks - 1) {              // accumulator fully read: hand the TMEM stage back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+      }
+      fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the bulk-copy engine
+      epi_bar_sync();
+      if (e0) {
+        const uint32_t sbuf = out_base + buf * (uint32_t)kStageBytes;
+        tma_store_4d(tmC, sbuf, nc, x0, y0, img);
+        bulk_commit();
+        bulk_wait_read<1>();               // the store that used the OTHER buffer has finished reading it
+        if (RES == 1) {                    // fetch the next chunk's residual into that buffer
+          int nn0 = n0, nx0 = x0, ny0 = y0, nimg = img, ncol = nc + 64;
+          bool have = true;
+          if (c == nchunks - 1) {
+            const int nt = tile + gridDim.x;
+            have = nt < total_tiles;
+            if (have) { tile_coords(nt, nn0, nx0, ny0, nimg); ncol = nn0; }
+          }
+          if (have) {
+            mbar_expect_tx(rfull0 + 8u * (buf ^ 1u), (uint32_t)kStageBytes);
+            tma_load_4d(out_base + (buf ^ 1u) * (uint32_t)kStageBytes, tmR, rfull0 + 8u * (buf ^ 1u), ncol, nx0, ny0, nimg);
+          }
+        }
+      }
+    }
+    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+  }
+  if (e0) bulk_wait<0>();
+}
 
 }  // namespace cg
 
@@ -287,119 +415,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row = q * 32 + lane;          // accumulator row = pixel inside the tile
     int acc = 0; uint32_t acc_phase = 0;
     if (p.tma_out) {
-      // ---- staged epilogue: TMEM -> regs -> (+bias, +residual, ReLU) -> fp16 -> swizzled smem -> TMA store.
-      // The residual sub-tile (same geometry as the output sub-tile) is TMA-loaded into the very staging
-      // buffer the result is then written to, one 64-channel chunk ahead of its use.
-      const bool e0 = (threadIdx.x == 64);   // warp 2, lane 0: issues all bulk copies of this CTA's epilogue
-      const int nchunks = (min(BN, p.cout) + 63) / 64;
-      auto tile_coords = [&](int tile, int& n0, int& x0, int& y0, int& img) {
-        const int nt = tile % p.tiles_n;
-        const int mt = tile / p.tiles_n;
-        n0 = nt * BN;
-        x0 = (mt % p.tiles_x) * p.tw;
-        y0 = ((mt / p.tiles_x) % p.tiles_y) * p.th;
-        img = mt / (p.tiles_x * p.tiles_y);
-      };
-      uint32_t cc = 0;                       // chunk counter of this CTA (buffer = cc & 1)
-      if (p.tma_res && e0 && (int)blockIdx.x < total_tiles) {
-        cg::prefetch_tmap(&tmC); cg::prefetch_tmap(&tmR);
-        int n0, x0, y0, img;
-        tile_coords(blockIdx.x, n0, x0, y0, img);
-        cg::mbar_expect_tx(rfull_bar(0), (uint32_t)C::kOutStageBytes);
-        cg::tma_load_4d(out_base, &tmR, rfull_bar(0), n0, x0, y0, img);
-      }
-      const uint32_t row_off = (uint32_t)row * 128u;
-      const uint32_t sw = (uint32_t)(row & 7);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int n0, x0, y0, img;
-        tile_coords(tile, n0, x0, y0, img);
-        const int x = x0 + (row % p.tw), y = y0 + (row / p.tw);
-        const bool pix_ok = (x < p.w_out) && (y < p.h_out);
-        const __half* res_row = nullptr;
-        if (p.res_mode == 2 && pix_ok)       // FPN top-down: nearest 2x up-sampled residual, gathered directly
-          res_row = p.residual + (((size_t)img * p.res_h + (y >> 1)) * (size_t)p.res_w + (x >> 1)) * (size_t)p.res_ld;
-        cg::mbar_wait(tfull_bar(acc), acc_phase);
-        cg::tc_fence_after();
-        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-        #pragma unroll 1
-        for (int c = 0; c < nchunks; ++c, ++cc) {
-          const uint32_t buf = cc & 1u;
-          const uint32_t sbuf = out_base + buf * (uint32_t)C::kOutStageBytes;
-          const int nc = n0 + c * 64;
-          if (p.tma_res) {
-            cg::mbar_wait(rfull_bar(buf), (cc >> 1) & 1u);      // residual chunk has landed (also: buffer is free)
-          } else {
-            cg::epi_bar_sync();                                  // e0 has seen the store that last read this buffer finish
-          }
-          #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t v[32];
-            cg::tmem_ld32(t_addr + (uint32_t)(c * 64 + hh * 32), v);
-            cg::tmem_ld_wait();
-            #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int n = nc + hh * 32 + g * 8;
-              const uint32_t saddr = sbuf + row_off + ((((uint32_t)(hh * 4 + g)) ^ sw) << 4);
-              float f[8];
-              #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
-              if (p.bias && n < p.cout) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + 1);
-                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-              }
-              if (p.tma_res) {
-                const uint4 rv = cg::lds128(saddr);
-                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-                #pragma unroll
-                for (int e = 0; e < 4; ++e) { float2 r2 = __half22float2(rh[e]); f[2 * e] += r2.x; f[2 * e + 1] += r2.y; }
-              } else if (res_row) {
-                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_row + n));
-                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-                #pragma unroll
-                for (int e = 0; e < 4; ++e) { float2 r2 = __half22float2(rh[e]); f[2 * e] += r2.x; f[2 * e + 1] += r2.y; }
-              }
-              if (p.relu) {
-                #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
-              }
-              uint4 ov;
-              __half2* oh = reinterpret_cast<__half2*>(&ov);
-              #pragma unroll
-              for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
-              cg::sts128(saddr, ov);
-            }
-          }
-          if (c == nchunks - 1) {            // accumulator fully read: hand the TMEM stage back to the MMA warp
-            cg::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) cg::mbar_arrive(tempty_bar(acc));
-          }
-          cg::fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the bulk-copy engine
-          cg::epi_bar_sync();
-          if (e0) {
-            cg::tma_store_4d(&tmC, sbuf, nc, x0, y0, img);
-            cg::bulk_commit();
-            cg::bulk_wait_read<1>();         // the store that used the OTHER buffer has finished reading it
-            if (p.tma_res) {                 // fetch the next chunk's residual into that buffer
-              int nn0 = n0, nx0 = x0, ny0 = y0, nimg = img, ncol = nc + 64;
-              bool have = true;
-              if (c == nchunks - 1) {
-                const int nt = tile + gridDim.x;
-                have = nt < total_tiles;
-                if (have) { tile_coords(nt, nn0, nx0, ny0, nimg); ncol = nn0; }
-              }
-              if (have) {
-                cg::mbar_expect_tx(rfull_bar(buf ^ 1u), (uint32_t)C::kOutStageBytes);
-                cg::tma_load_4d(out_base + (buf ^ 1u) * (uint32_t)C::kOutStageBytes, &tmR, rfull_bar(buf ^ 1u), ncol, nx0, ny0, nimg);
-              }
-            }
-          }
-        }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-      }
-      if (e0) cg::bulk_wait<0>();
+      const uint32_t rf0 = rfull_bar(0), tf0 = tfull_bar(0), te0 = tempty_bar(0);
+      uint8_t* out_gen = smem_gen + C::kStages * C::kStageBytes;
+      float* bias_gen = reinterpret_cast<float*>(out_gen + C::kOutBytes + 256);
+      if (p.tma_res) cg::epilogue_staged<BN, 1>(p, &tmC, &tmR, out_gen, out_base, bias_gen, rf0, tf0, te0, tmem_base, total_tiles, warp, lane);
+      else if (p.res_mode == 2) cg::epilogue_staged<BN, 2>(p, &tmC, &tmR, out_gen, out_base, bias_gen, rf0, tf0, te0, tmem_base, total_tiles, warp, lane);
+      else cg::epilogue_staged<BN, 0>(p, &tmC, &tmR, out_gen, out_base, bias_gen, rf0, tf0, te0, tmem_base, total_tiles, warp, lane);
     } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % p.tiles_n;

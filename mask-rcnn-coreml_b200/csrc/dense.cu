@@ -2,6 +2,7 @@
 // TMA tensor-map construction, tile-shape selection and launch.
 #include "dense.h"
 #include <string.h>
+#include <stdlib.h>
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,

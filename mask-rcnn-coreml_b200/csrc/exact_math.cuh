@@ -77,6 +77,8 @@ __device__ __forceinline__ float iou_rect(const RectD& a, const RectD& b) {
   double ix1 = a.maxx < b.maxx ? a.maxx : b.maxx;
   double iy1 = a.maxy < b.maxy ? a.maxy : b.maxy;
   double ih = __dsub_rn(iy1, iy0), iw = __dsub_rn(ix1, ix0);
+  // disjoint boxes: inter = 0 -> 0 / union = +0 exactly; skip the fp64 multiply / divide (most pairs)
+  if (!(ih > 0.0) || !(iw > 0.0)) { if (!(ih != ih) && !(iw != iw)) return 0.0f; }
   ih = ih < 0.0 ? 0.0 : ih;
   iw = iw < 0.0 ? 0.0 : iw;
   double inter = __dmul_rn(ih, iw);

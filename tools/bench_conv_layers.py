@@ -57,6 +57,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--only", default="", help="comma separated substrings of layer tags to run")
     args = ap.parse_args()
     ctx = m.Context()
     st = torch.cuda.Stream()
@@ -65,6 +66,8 @@ def main():
     rows = []
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for tag, n, h, w, cin, cout, k, stride, count in layer_shapes(args.batch):
+        if args.only and not any(o in tag for o in args.only.split(",")):
+            continue
         pad = k // 2
         ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
         ldc = (cout + 7) // 8 * 8
