@@ -1,7 +1,8 @@
 // aux_kernels.cuh -- the memory-bound glue kernels of the dense pipeline
 // (everything that is not a convolution): image pre-processing, max-pool,
 // P6 subsampling, RPN softmax/reorder, classifier softmax+argmax, the mask
-// head's class-selected 1x1 + sigmoid, and boundary-layout conversions.
+// head's slot bookkeeping (its class-selected 1x1 + sigmoid is fused into the deconv epilogue, conv_gemm.cuh),
+// and boundary-layout conversions.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -146,42 +147,6 @@ __global__ void cls_post_kernel(const float* __restrict__ logits, int64_t total,
   if (lane < 4) out6[r * 6 + lane] = l[ncls + bi * 4 + lane];
   if (lane == 4) out6[r * 6 + 4] = (float)bi;
   if (lane == 5) out6[r * 6 + 5] = bv;
-}
-
-// Mask head tail (TimeDistributedMaskLayer.swift:58-89): only the detected class's
-// plane of the final 1x1 conv is needed, so compute just that one:
-//   out[d, y, x] = sigmoid(b[cls] + sum_c feat[d, y, x, c] * w[cls, c])
-// feat [D_total, S, S, C] f16; det [D_total, 6]; slot_src[d] = index of the valid
-// block that lands in slot d, or -1 (zero plane); cls_of[d] = class id for slot d.
-// One warp per output pixel.
-__global__ void mask_final_kernel(const __half* __restrict__ feat, const __half* __restrict__ w,
-                                  const float* __restrict__ bias, const int32_t* __restrict__ slot_valid,
-                                  const int32_t* __restrict__ slot_cls, int64_t total_pix, int SS, int C, int ncls,
-                                  float* __restrict__ out) {
-  const int64_t pidx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (pidx >= total_pix) return;
-  const int64_t d = pidx / SS;
-  if (!slot_valid[d]) { if (lane == 0) out[pidx] = 0.0f; return; }
-  int cls = slot_cls[d];
-  cls = cls < 0 ? 0 : (cls >= ncls ? ncls - 1 : cls);
-  const __half* f = feat + pidx * C;
-  const __half* wc = w + (int64_t)cls * C;
-  float acc = 0.0f;
-  for (int c = lane * 8; c < C; c += 256) {
-    const uint4 fv = __ldg(reinterpret_cast<const uint4*>(f + c));
-    const uint4 wv = __ldg(reinterpret_cast<const uint4*>(wc + c));
-    const __half2* fh = reinterpret_cast<const __half2*>(&fv);
-    const __half2* wh = reinterpret_cast<const __half2*>(&wv);
-    #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 a = __half22float2(fh[k]), b = __half22float2(wh[k]);
-      acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc);
-    }
-  }
-  #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) out[pidx] = 1.0f / (1.0f + expf(-(acc + bias[cls])));
 }
 
 // Slot bookkeeping of TimeDistributedMaskLayer (:52, :58-60, :71, :87-89):

@@ -49,6 +49,14 @@ struct ConvGemmParams {
   int deconv_c;
   int tma_out;                 // 1: fp16 NHWC output staged in smem and written with TMA stores (cout % 64 == 0)
   int tma_res;                 // 1: residual (res_mode 1) tiles fetched with TMA into the same staging buffers
+  int nstages;                 // depth of the operand ring (A+B tiles), chosen per layer by the host
+  int nbuf_log2;               // log2 of the number of 16 KB output / residual staging buffers (1 or 2)
+  int maskdot;                 // 1: mask-head tail fused into the deconv epilogue (see epilogue_maskdot)
+  const int32_t* md_valid;     // [n_img] slot is a real detection
+  const int32_t* md_cls;       // [n_img] class id of the slot
+  const __half* md_w;          // [md_ncls][deconv_c] final 1x1 weights
+  const float* md_b;           // [md_ncls]
+  int md_ncls;
   const float* bias;           // [cout] or nullptr
   const __half* residual;
   void* out;
@@ -176,11 +184,17 @@ template <int BN> struct Cfg {
   static constexpr int kABytes = CG_BM * CG_BK * 2;          // 16 KB
   static constexpr int kBBytes = BN * CG_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN >= 256) ? 4 : ((BN >= 128) ? 6 : 8);
+  // shared memory = operand ring (nstages x kStageBytes) + output/residual staging (nbuf x 16 KB) + barriers + bias
+  // tile; the split between ring depth and staging depth is chosen per layer (host: conv_plan_build):
+  //   compute-bound layers   deep ring,  2 staging buffers
+  //   memory-bound layers    short ring, 4 staging buffers (residual prefetched 3 chunks ahead, 3 stores in flight)
+  static constexpr int kStagesDeep = (BN >= 256) ? 4 : ((BN >= 128) ? 6 : 8);
+  static constexpr int kStagesShort = (BN >= 256) ? 3 : ((BN >= 128) ? 5 : 6);
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // BN in {32,64,128,256} -> power of two
   static constexpr int kOutStageBytes = CG_BM * 64 * 2;           // one 128-pixel x 64-channel fp16 sub-tile (SWIZZLE_128B)
-  static constexpr int kOutBytes = 2 * kOutStageBytes;            // double buffered
-  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias tile*/;
+  static constexpr int kMaxRingPlusOut = (kStagesDeep * kStageBytes + 2 * kOutStageBytes) > (kStagesShort * kStageBytes + 4 * kOutStageBytes)
+                                             ? (kStagesDeep * kStageBytes + 2 * kOutStageBytes) : (kStagesShort * kStageBytes + 4 * kOutStageBytes);
+  static constexpr int kSmemBytes = kMaxRingPlusOut + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias tile*/;
 };
 
 // ---- staged epilogue (fp16 NHWC outputs): TMEM -> regs -> (+bias, +residual, ReLU) -> fp16 -> swizzled smem ->
@@ -194,6 +208,7 @@ __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, const C
                                                 uint32_t rfull0, uint32_t tfull0, uint32_t tempty0,
                                                 uint32_t tmem_base, int total_tiles, int warp, int lane) {
   constexpr int kStageBytes = CG_BM * 64 * 2;
+  const uint32_t nb_log2 = (uint32_t)p.nbuf_log2, nb_mask = (1u << nb_log2) - 1u;
   const int q = warp & 3;
   const int row = q * 32 + lane;
   const bool e0 = (threadIdx.x == 64);     // warp 2, lane 0: issues all bulk copies of this CTA's epilogue
@@ -207,16 +222,23 @@ __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, const C
     y0 = ((mt / p.tiles_x) % p.tiles_y) * p.th;
     img = mt / (p.tiles_x * p.tiles_y);
   };
-  uint32_t cc = 0;                         // chunk counter of this CTA (buffer = cc & 1)
+  uint32_t cc = 0;                         // chunk counter of this CTA (staging buffer = cc & nb_mask)
   int bias_n0 = -1;
   int acc = 0; uint32_t acc_phase = 0;
-  if (e0) { prefetch_tmap(tmC); if (RES == 1) prefetch_tmap(tmR); }
-  if (RES == 1 && e0 && (int)blockIdx.x < total_tiles) {
+  // residual prefetch (RES == 1): chunk j of this CTA = tile blockIdx.x + (j / nchunks) * gridDim.x, chunk j % nchunks
+  const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const uint32_t my_chunks = (uint32_t)(my_tiles * nchunks);
+  auto load_residual = [&](uint32_t j) {
+    if (j >= my_chunks) return;
+    const int t = blockIdx.x + (int)(j / (uint32_t)nchunks) * gridDim.x;
     int n0, x0, y0, img;
-    tile_coords(blockIdx.x, n0, x0, y0, img);
-    mbar_expect_tx(rfull0, (uint32_t)kStageBytes);
-    tma_load_4d(out_base, tmR, rfull0, n0, x0, y0, img);
-  }
+    tile_coords(t, n0, x0, y0, img);
+    const uint32_t b = j & nb_mask;
+    mbar_expect_tx(rfull0 + 8u * b, (uint32_t)kStageBytes);
+    tma_load_4d(out_base + b * (uint32_t)kStageBytes, tmR, rfull0 + 8u * b, n0 + (int)(j % (uint32_t)nchunks) * 64, x0, y0, img);
+  };
+  if (e0) { prefetch_tmap(tmC); if (RES == 1) prefetch_tmap(tmR); }
+  if (RES == 1 && e0) for (uint32_t j = 0; j < nb_mask; ++j) load_residual(j);     // prefetch distance = nbuf - 1 chunks
   const uint32_t row_off = (uint32_t)row * 128u;
   const uint32_t sw = (uint32_t)(row & 7);
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -240,10 +262,10 @@ __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, const C
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
     #pragma unroll 1
     for (int c = 0; c < nchunks; ++c, ++cc) {
-      const uint32_t buf = cc & 1u;
+      const uint32_t buf = cc & nb_mask;
       uint8_t* srow = out_gen + buf * kStageBytes + row_off;
       const int nc = n0 + c * 64;
-      if (RES == 1) mbar_wait(rfull0 + 8u * buf, (cc >> 1) & 1u);   // residual chunk has landed (so the buffer is free, too)
+      if (RES == 1) mbar_wait(rfull0 + 8u * buf, (cc >> nb_log2) & 1u);   // residual chunk has landed (so the buffer is free, too)
       else epi_bar_sync();                                            // e0 has seen the store that last read this buffer finish
       #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
@@ -290,25 +312,84 @@ __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, const C
         const uint32_t sbuf = out_base + buf * (uint32_t)kStageBytes;
         tma_store_4d(tmC, sbuf, nc, x0, y0, img);
         bulk_commit();
-        bulk_wait_read<1>();               // the store that used the OTHER buffer has finished reading it
-        if (RES == 1) {                    // fetch the next chunk's residual into that buffer
-          int nn0 = n0, nx0 = x0, ny0 = y0, nimg = img, ncol = nc + 64;
-          bool have = true;
-          if (c == nchunks - 1) {
-            const int nt = tile + gridDim.x;
-            have = nt < total_tiles;
-            if (have) { tile_coords(nt, nn0, nx0, ny0, nimg); ncol = nn0; }
-          }
-          if (have) {
-            mbar_expect_tx(rfull0 + 8u * (buf ^ 1u), (uint32_t)kStageBytes);
-            tma_load_4d(out_base + (buf ^ 1u) * (uint32_t)kStageBytes, tmR, rfull0 + 8u * (buf ^ 1u), ncol, nx0, ny0, nimg);
-          }
+        if (RES == 1) {
+          bulk_wait_read<1>();             // store cc-1 has finished reading its buffer ...
+          load_residual(cc + nb_mask);     // ... which is the buffer of chunk cc + nbuf - 1: fetch that chunk's residual
+        } else if (nb_mask == 1u) {
+          bulk_wait_read<1>();             // buffer of chunk cc+1 (used by store cc-1) is free
+        } else {
+          bulk_wait_read<3>();             // 4 buffers: buffer of chunk cc+1 was used by store cc-3
         }
       }
     }
     if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
   }
   if (e0) bulk_wait<0>();
+}
+
+// ---- mask-head tail fused into the 2x2 stride-2 transposed convolution (TimeDistributedMaskLayer.swift:58-89):
+// N tile nt = sub-pixel (dy,dx) with all deconv_c channels; per output pixel
+//   m = sigmoid(b[cls] + sum_c fp16(relu(acc[c] + bias[c])) * w[cls][c])
+// for the class of the detection in that slot only (the reference computes all 81 planes and keeps one).  The
+// deconvolution output itself is never written.  Invalid slots produce 0.
+template <int BN>
+__device__ __forceinline__ void epilogue_maskdot(const ConvGemmParams& p, float* bias_gen, uint32_t tfull0, uint32_t tempty0,
+                                                 uint32_t tmem_base, int total_tiles, int warp, int lane) {
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+  float* w_gen = bias_gen + BN;
+  float* out = reinterpret_cast<float*>(p.out);
+  int acc = 0; uint32_t acc_phase = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int nt = tile % p.tiles_n;
+    const int mt = tile / p.tiles_n;
+    const int x = (mt % p.tiles_x) * p.tw + (row % p.tw);
+    const int y = ((mt / p.tiles_x) % p.tiles_y) * p.th + (row / p.tw);
+    const int img = mt / (p.tiles_x * p.tiles_y);
+    const bool pix_ok = (x < p.w_out) && (y < p.h_out);
+    const int valid = __ldg(p.md_valid + img);
+    int cls = __ldg(p.md_cls + img);
+    cls = cls < 0 ? 0 : (cls >= p.md_ncls ? p.md_ncls - 1 : cls);
+    epi_bar_sync();                        // everybody is done with the previous tile's bias / weight rows
+    for (int i = threadIdx.x - 64; i < BN; i += 128) {
+      bias_gen[i] = __ldg(p.bias + nt * BN + i);
+      w_gen[i] = __half2float(__ldg(p.md_w + (size_t)cls * p.deconv_c + i));
+    }
+    epi_bar_sync();
+    mbar_wait(tfull0 + 8u * acc, acc_phase);
+    tc_fence_after();
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+    float dot = 0.0f;
+    #pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_addr + (uint32_t)(c * 32), v);
+      float4 bq[8], wq[8];
+      #pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        bq[g] = reinterpret_cast<const float4*>(bias_gen + c * 32)[g];
+        wq[g] = reinterpret_cast<const float4*>(w_gen + c * 32)[g];
+      }
+      tmem_ld_wait();
+      #pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float a0 = __half2float(__float2half_rn(fmaxf(__uint_as_float(v[4 * g + 0]) + bq[g].x, 0.0f)));
+        const float a1 = __half2float(__float2half_rn(fmaxf(__uint_as_float(v[4 * g + 1]) + bq[g].y, 0.0f)));
+        const float a2 = __half2float(__float2half_rn(fmaxf(__uint_as_float(v[4 * g + 2]) + bq[g].z, 0.0f)));
+        const float a3 = __half2float(__float2half_rn(fmaxf(__uint_as_float(v[4 * g + 3]) + bq[g].w, 0.0f)));
+        dot = fmaf(a0, wq[g].x, dot); dot = fmaf(a1, wq[g].y, dot); dot = fmaf(a2, wq[g].z, dot); dot = fmaf(a3, wq[g].w, dot);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+    if (pix_ok) {
+      const int dy = nt >> 1, dx = nt & 1;
+      const float m = valid ? 1.0f / (1.0f + expf(-(dot + __ldg(p.md_b + cls)))) : 0.0f;
+      out[((size_t)img * (2 * p.h_out) + (2 * y + dy)) * (size_t)(2 * p.w_out) + (2 * x + dx)] = m;
+    }
+    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+  }
 }
 
 }  // namespace cg
@@ -322,17 +403,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   // 1024-B aligned operand ring (SWIZZLE_128B requirement)
   const uint32_t smem_base = (cg::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t out_base = smem_base + C::kStages * C::kStageBytes;     // 2 x 16 KB output / residual staging
-  const uint32_t bar_base = out_base + C::kOutBytes;
-  // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; the TMEM base slot; res_full[2]
+  const int nst = p.nstages;
+  const uint32_t ring_bytes = (uint32_t)nst * (uint32_t)C::kStageBytes;
+  const uint32_t out_bytes = (uint32_t)C::kOutStageBytes << p.nbuf_log2;
+  const uint32_t out_base = smem_base + ring_bytes;                      // nbuf x 16 KB output / residual staging
+  const uint32_t bar_base = out_base + out_bytes;
+  // barriers (fixed layout): full[8] @0, empty[8] @64, tmem_full[2] @128, tmem_empty[2] @144, TMEM base slot @160, res_full[4] @168
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4);
-  auto rfull_bar = [&](int b) { return bar_base + 8u * (2 * C::kStages + 5 + b); };
+  auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
+  auto tfull_bar = [&](int a) { return bar_base + 128u + 8u * a; };
+  auto tempty_bar = [&](int a) { return bar_base + 144u + 8u * a; };
+  const uint32_t tmem_slot = bar_base + 160u;
+  auto rfull_bar = [&](int b) { return bar_base + 168u + 8u * b; };
   uint8_t* smem_gen = smem_raw + (smem_base - cg::smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + C::kStages * C::kStageBytes + C::kOutBytes + 8 * (2 * C::kStages + 4));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + ring_bytes + out_bytes + 160u);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -340,8 +424,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     cg::prefetch_tmap(&tmA);
     cg::prefetch_tmap(&tmB);
-    for (int s = 0; s < C::kStages; ++s) { cg::mbar_init(full_bar(s), 1); cg::mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { cg::mbar_init(tfull_bar(a), 1); cg::mbar_init(tempty_bar(a), 4); cg::mbar_init(rfull_bar(a), 1); }
+    for (int s = 0; s < nst; ++s) { cg::mbar_init(full_bar(s), 1); cg::mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { cg::mbar_init(tfull_bar(a), 1); cg::mbar_init(tempty_bar(a), 4); }
+    for (int b = 0; b < 4; ++b) cg::mbar_init(rfull_bar(b), 1);
     cg::fence_barrier_init();
   }
   if (warp == 1) cg::tmem_alloc(tmem_slot, C::kTmemCols);
@@ -376,7 +461,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t b_dst = a_dst + C::kABytes;
             cg::tma_load_4d(a_dst, &tmA, full_bar(stage), cc * CG_BK, xi, yi, img);
             cg::tma_load_2d(b_dst, &tmB, full_bar(stage), t * p.cin + cc * CG_BK, n0);
-            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+            if (++stage == nst) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -403,7 +488,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             cg::umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
           }
           cg::umma_commit(empty_bar(stage));                   // frees the smem slot when the MMAs retire
-          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == nst) { stage = 0; phase ^= 1u; }
         }
         cg::umma_commit(tfull_bar(acc));                       // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -414,10 +499,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;          // accumulator row = pixel inside the tile
     int acc = 0; uint32_t acc_phase = 0;
-    if (p.tma_out) {
+    if (p.maskdot) {
+      float* bias_gen = reinterpret_cast<float*>(smem_gen + ring_bytes);       // bias + class weights live in the (unused) staging area
+      cg::epilogue_maskdot<BN>(p, bias_gen, tfull_bar(0), tempty_bar(0), tmem_base, total_tiles, warp, lane);
+    } else if (p.tma_out) {
       const uint32_t rf0 = rfull_bar(0), tf0 = tfull_bar(0), te0 = tempty_bar(0);
-      uint8_t* out_gen = smem_gen + C::kStages * C::kStageBytes;
-      float* bias_gen = reinterpret_cast<float*>(out_gen + C::kOutBytes + 256);
+      uint8_t* out_gen = smem_gen + ring_bytes;
+      float* bias_gen = reinterpret_cast<float*>(out_gen + out_bytes + 256);
       if (p.tma_res) cg::epilogue_staged<BN, 1>(p, &tmC, &tmR, out_gen, out_base, bias_gen, rf0, tf0, te0, tmem_base, total_tiles, warp, lane);
       else if (p.res_mode == 2) cg::epilogue_staged<BN, 2>(p, &tmC, &tmR, out_gen, out_base, bias_gen, rf0, tf0, te0, tmem_base, total_tiles, warp, lane);
       else cg::epilogue_staged<BN, 0>(p, &tmC, &tmR, out_gen, out_base, bias_gen, rf0, tf0, te0, tmem_base, total_tiles, warp, lane);

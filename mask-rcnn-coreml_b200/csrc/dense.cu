@@ -137,6 +137,22 @@ int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan) {
   plan->tmC = plan->tmB; plan->tmR = plan->tmB;      // valid placeholders when the staged epilogue is off
   p.tma_out = (!L.no_tma_epilogue && !L.out_f32 && !L.deconv && (L.cout % 64) == 0 && bn >= 64) ? 1 : 0;
   p.tma_res = (p.tma_out && p.res_mode == 1) ? 1 : 0;
+  p.maskdot = L.maskdot;
+  if (L.maskdot) {
+    MRCNN_REQUIRE(ctx, L.deconv && L.deconv_c == 256 && bn == 256 && L.bias && L.md_valid && L.md_cls && L.md_w && L.md_b && L.md_ncls > 0,
+                  "conv: the fused mask tail needs a 256-channel deconvolution with bias and the slot / class-weight arrays");
+    p.md_valid = L.md_valid; p.md_cls = L.md_cls; p.md_w = L.md_w; p.md_b = L.md_b; p.md_ncls = L.md_ncls;
+  }
+  // ring depth vs staging depth (see cg::Cfg): memory-bound layers (few K blocks per tile, or a TMA-fetched residual)
+  // trade ring stages for staging buffers so that the residual is prefetched further ahead and more stores are in flight
+  {
+    const int nkb = ntaps * (L.cin / CG_BK);
+    const bool deep_staging = p.tma_out && (p.tma_res || nkb <= 4);
+    const int deep[4] = {8, 8, 6, 4}, shrt[4] = {6, 6, 5, 3};     // BN = 32, 64, 128, 256
+    const int bi = bn == 32 ? 0 : (bn == 64 ? 1 : (bn == 128 ? 2 : 3));
+    p.nstages = deep_staging ? shrt[bi] : deep[bi];
+    p.nbuf_log2 = deep_staging ? 2 : 1;
+  }
   if (p.tma_out) {
     cuuint64_t cdims[4] = {(cuuint64_t)L.cout, (cuuint64_t)p.w_out, (cuuint64_t)p.h_out, (cuuint64_t)L.n};
     cuuint64_t cstr[3] = {(cuuint64_t)p.ldc * 2, (cuuint64_t)p.ldc * 2 * p.w_out, (cuuint64_t)p.ldc * 2 * p.w_out * p.h_out};

@@ -28,6 +28,13 @@ struct ConvLaunch {
   int ldc = 0;                   // 0 -> round_up(cout, 8)
   int tw = 0, th = 0, bn = 0;    // 0 -> auto
   int no_tma_epilogue = 0;       // force the direct-store epilogue (tests)
+  // mask-head tail fused into the deconv epilogue (needs deconv = 1, deconv_c == bn == 256): out = f32 [n, 2h, 2w]
+  int maskdot = 0;
+  const int32_t* md_valid = nullptr;
+  const int32_t* md_cls = nullptr;
+  const __half* md_w = nullptr;
+  const float* md_b = nullptr;
+  int md_ncls = 0;
 };
 
 struct ConvPlan {

@@ -40,6 +40,7 @@ struct DenseModel {
   std::map<std::string, Buf> bufs;
   std::map<int, std::shared_ptr<Graph>> g_backbone;       // keyed by batch
   std::map<int64_t, std::shared_ptr<Graph>> g_cls, g_mask; // keyed by total rois / detections
+  std::map<int64_t, std::shared_ptr<ConvPlan>> mask_last;  // deconv + fused mask tail (output pointer patched per call)
   int lvl_h[5] = {0}, lvl_w[5] = {0};
   int64_t n_anchors = 0;
   const uint8_t* rgb = nullptr;      // input of the running predict (device pointer, not owned)
@@ -61,7 +62,7 @@ static int get_buf(mrcnn_ctx* ctx, const char* name, size_t bytes, void** out) {
       // growing a buffer would invalidate the tensor maps of the cached graphs
       MRCNN_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
       cudaFree(b.p); b.p = nullptr;
-      m->g_backbone.clear(); m->g_cls.clear(); m->g_mask.clear();
+      m->g_backbone.clear(); m->g_cls.clear(); m->g_mask.clear(); m->mask_last.clear();
     }
     MRCNN_CUDA_TRY(ctx, cudaMalloc(&b.p, bytes));
     b.bytes = bytes;
@@ -83,7 +84,7 @@ int dense_load_weights(mrcnn_ctx* ctx, int which, const void* blob, size_t bytes
   MRCNN_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   WeightSet& w = m->ws[which];
   cudaFree(w.d_base); w.d_base = nullptr; w.t.clear(); w.loaded = false;
-  m->g_backbone.clear(); m->g_cls.clear(); m->g_mask.clear();
+  m->g_backbone.clear(); m->g_cls.clear(); m->g_mask.clear(); m->mask_last.clear();
   MRCNN_CUDA_TRY(ctx, cudaMalloc(&w.d_base, bytes));
   MRCNN_CUDA_TRY(ctx, cudaMemcpy(w.d_base, blob, bytes, cudaMemcpyHostToDevice));
   w.bytes = bytes;
@@ -416,12 +417,11 @@ static int mask_graph(mrcnn_ctx* ctx, int64_t M, std::shared_ptr<Graph>* out_gra
   const int P = cfg.pool_size_mask;
   const int64_t cap = (int64_t)(cfg.max_batch > 1 ? cfg.max_batch : 1) * cfg.max_detections;
   const int64_t MM = M > cap ? M : cap;
-  __half *pooled, *ma, *mb, *up;
+  __half *pooled, *ma, *mb;
   int32_t *valid, *slot_valid, *slot_cls;
   TRY(get_buf(ctx, "pooled_mask", (size_t)MM * P * P * 256 * 2, (void**)&pooled));
   TRY(get_buf(ctx, "mask_a", (size_t)MM * P * P * 256 * 2, (void**)&ma));
   TRY(get_buf(ctx, "mask_b", (size_t)MM * P * P * 256 * 2, (void**)&mb));
-  TRY(get_buf(ctx, "mask_up", (size_t)MM * 4 * P * P * 256 * 2, (void**)&up));
   TRY(get_buf(ctx, "mask_valid", (size_t)MM * 4, (void**)&valid));
   TRY(get_buf(ctx, "mask_slot_valid", (size_t)MM * 4, (void**)&slot_valid));
   TRY(get_buf(ctx, "mask_slot_cls", (size_t)MM * 4, (void**)&slot_cls));
@@ -435,20 +435,28 @@ static int mask_graph(mrcnn_ctx* ctx, int64_t M, std::shared_ptr<Graph>* out_gra
     TRY(add_conv(ctx, *g, 2, A));
     x = y;
   }
-  // 2x2 stride-2 transposed conv = GEMM with 4*256 outputs + pixel-shuffle store
-  WTensor w, b;
+  // 2x2 stride-2 transposed conv (GEMM with 4*256 outputs, one N tile per sub-pixel) + ReLU, with the final
+  // class-selected 1x1 conv + sigmoid fused into its epilogue: the (M, 2P, 2P, 256) tensor is never materialised.
+  WTensor w, b, wf, bf;
   TRY(find_w(ctx, 2, "mask.deconv.w", 0, &w));
   TRY(find_w(ctx, 2, "mask.deconv.b", 1, &b));
+  TRY(find_w(ctx, 2, "mask.final.w", 0, &wf));
+  TRY(find_w(ctx, 2, "mask.final.b", 1, &bf));
   MRCNN_REQUIRE(ctx, w.dims[0] == 1024 && w.dims[1] == 1 && w.dims[2] == 1 && w.dims[3] == 256 && b.dims[0] == 1024,
                 "mask.deconv.w must be [4*256,1,1,256] with a [1024] bias (bias repeated per sub-pixel)");
+  MRCNN_REQUIRE(ctx, wf.dims[0] == cfg.num_classes && wf.dims[3] == 256 && bf.dims[0] == cfg.num_classes,
+                "mask.final.w must be [num_classes,1,1,256]");
   {
     ConvLaunch L;
     L.x = x; L.n = (int)M; L.h_in = P; L.w_in = P; L.cin = 256;
     L.w = (const __half*)w.d; L.cout = 1024; L.kh = 1; L.kw = 1; L.bias = (const float*)b.d; L.relu = 1;
-    L.deconv = 1; L.deconv_c = 256; L.out = up; L.ldc = 256; L.bn = 256;
+    L.deconv = 1; L.deconv_c = 256; L.out = slot_valid /* patched per call */; L.out_f32 = 1; L.ldc = 256; L.bn = 256;
+    L.maskdot = 1; L.md_valid = slot_valid; L.md_cls = slot_cls; L.md_w = (const __half*)wf.d; L.md_b = (const float*)bf.d;
+    L.md_ncls = cfg.num_classes;
     auto plan = std::make_shared<ConvPlan>();
     TRY(conv_plan_build(ctx, L, plan.get()));
-    g->push_back([plan](mrcnn_ctx* c) { return conv_plan_run(c, *plan); });
+    plan->flops += 2.0 * M * 4 * P * P * 256.0;      // the fused class-selected 1x1
+    m->mask_last[M] = plan;
   }
   m->g_mask[M] = g;
   *out_graph = g;
@@ -457,24 +465,19 @@ static int mask_graph(mrcnn_ctx* ctx, int64_t M, std::shared_ptr<Graph>* out_gra
 
 static int mask_tail(mrcnn_ctx* ctx, int batch, int D, const float* d_det, float* d_out) {
   DenseModel* m = model_of(ctx);
-  const mrcnn_config& cfg = ctx->cfg;
-  const int S = 2 * cfg.pool_size_mask;
-  WTensor w, b;
-  TRY(find_w(ctx, 2, "mask.final.w", 0, &w));
-  TRY(find_w(ctx, 2, "mask.final.b", 1, &b));
-  MRCNN_REQUIRE(ctx, w.dims[0] == cfg.num_classes && w.dims[3] == 256, "mask.final.w must be [num_classes,1,1,256]");
+  const int64_t M = (int64_t)batch * D;
+  auto it = m->mask_last.find(M);
+  MRCNN_REQUIRE(ctx, it != m->mask_last.end(), "mask head not built for this batch");
   const int32_t* valid = (const int32_t*)m->bufs["mask_valid"].p;
   int32_t* slot_valid = (int32_t*)m->bufs["mask_slot_valid"].p;
   int32_t* slot_cls = (int32_t*)m->bufs["mask_slot_cls"].p;
-  const __half* up = (const __half*)m->bufs["mask_up"].p;
-  const int64_t total_pix = (int64_t)batch * D * S * S;
-  ProfScope ps(ctx, PROF_GLUE, (double)total_pix * (512.0 + 4.0));
-  mask_slots_kernel<<<batch, 32, 0, ctx->stream>>>(valid, d_det, D, slot_valid, slot_cls);
-  MRCNN_LAUNCH_CHECK(ctx);
-  mask_final_kernel<<<grid1d(total_pix * 32, 256), 256, 0, ctx->stream>>>(up, (const __half*)w.d, (const float*)b.d, slot_valid,
-                                                                          slot_cls, total_pix, S * S, 256, cfg.num_classes, d_out);
-  MRCNN_LAUNCH_CHECK(ctx);
-  return MRCNN_OK;
+  {
+    ProfScope ps(ctx, PROF_GLUE, (double)M * 40.0);
+    mask_slots_kernel<<<batch, 32, 0, ctx->stream>>>(valid, d_det, D, slot_valid, slot_cls);
+    MRCNN_LAUNCH_CHECK(ctx);
+  }
+  it->second->p.out = d_out;
+  return conv_plan_run(ctx, *it->second);
 }
 
 // ------------------------------------------------------------------------------
