@@ -180,7 +180,7 @@ def run_reference(args):
         kind_cores = 1
     ms = 1e3 * float(np.mean(times))
     v = 1e3 / ms
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": {"workload": workload, "image": "1024x1024", "rois": 1000},
@@ -428,7 +428,11 @@ def run_ours(args):
             wl.step_e2e()
     e2e_ms = timed(wl.step_e2e, args.steps)
 
+    if world > 1:
+        dist.barrier()
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     peaks = load_peaks()
     ms_step = total_ms / args.steps
@@ -453,7 +457,9 @@ def run_ours(args):
         line.update(wl.extra_rooflines(prof, peaks))
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = wl.cpu_baseline() if hasattr(wl, "cpu_baseline") else default_cpu_baseline(m)
-    print(json.dumps(line))
+    emit(line)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def default_cpu_baseline(m):
@@ -467,7 +473,24 @@ def default_cpu_baseline(m):
             "sample": "2 images (after 1 warm-up) of the same custom-layer workload, oracle/liboracle.so, single thread"}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter) was re-routed to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # C-level stdout of this process (e.g. "NCCL version ...") -> stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
