@@ -87,6 +87,21 @@ int mrcnn_create(const mrcnn_config* cfg, mrcnn_ctx** out_ctx) {
     return mrcnn_fail(nullptr, MRCNN_ECUDA, "mrcnn_create: cudaStreamCreate failed");
   }
   ctx->stream = ctx->own_stream;
+  {
+    // stream-ordered staging pool that never gives memory back between calls (the default pool releases at every sync)
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    uint64_t keep = UINT64_MAX;
+    if (cudaMemPoolCreate(&ctx->pool, &props) != cudaSuccess ||
+        cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess) {
+      cudaStreamDestroy(ctx->own_stream);
+      delete ctx;
+      return mrcnn_fail(nullptr, MRCNN_ECUDA, "mrcnn_create: cudaMemPoolCreate failed");
+    }
+  }
   int rc = MRCNN_OK;
   if (!ctx->anchors_path.empty()) {
     std::vector<char> buf;
@@ -127,6 +142,7 @@ void mrcnn_destroy(mrcnn_ctx* ctx) {
   cudaFree(ctx->d_roi_level);
   cudaFree(ctx->d_gather_send); cudaFree(ctx->d_gather_recv);
   for (auto& pr : ctx->prof_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }

@@ -22,6 +22,7 @@ struct mrcnn_ctx {
   int sm_count = MRCNN_SM_COUNT_FALLBACK;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaMemPool_t pool = nullptr;       // staging pool for host-pointer calls (keeps its memory between calls)
   std::string err;
   int64_t launches = 0;
 
@@ -170,7 +171,7 @@ struct Stager {
     if (!p || bytes == 0) return const_cast<void*>(p);
     if (is_device_ptr(p)) return const_cast<void*>(p);
     Staged s; s.host = const_cast<void*>(p); s.bytes = bytes; s.is_output = false;
-    if (cudaMallocAsync(&s.dev, bytes, ctx->stream) != cudaSuccess) { *st = MRCNN_ECUDA; return nullptr; }
+    if (cudaMallocFromPoolAsync(&s.dev, bytes, ctx->pool, ctx->stream) != cudaSuccess) { *st = MRCNN_ECUDA; return nullptr; }
     if (cudaMemcpyAsync(s.dev, p, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { *st = MRCNN_ECUDA; return nullptr; }
     items.push_back(s); any_host = true;
     return s.dev;
@@ -179,7 +180,7 @@ struct Stager {
     if (!p || bytes == 0) return p;
     if (is_device_ptr(p)) return p;
     Staged s; s.host = p; s.bytes = bytes; s.is_output = true;
-    if (cudaMallocAsync(&s.dev, bytes, ctx->stream) != cudaSuccess) { *st = MRCNN_ECUDA; return nullptr; }
+    if (cudaMallocFromPoolAsync(&s.dev, bytes, ctx->pool, ctx->stream) != cudaSuccess) { *st = MRCNN_ECUDA; return nullptr; }
     items.push_back(s); any_host = true;
     return s.dev;
   }

@@ -435,6 +435,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   cg::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps
+  // the tail of the previous kernel in the stream; from here on this grid reads what that kernel wrote.  The
+  // trigger comes after the wait, so a dependent grid can only be scheduled once every CTA of this grid is running.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
   const int tiles_m = p.n_img * p.tiles_y * p.tiles_x;
   const int total_tiles = tiles_m * p.tiles_n;
   const int cin_chunks = p.cin / CG_BK;

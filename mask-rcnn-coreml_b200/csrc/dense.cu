@@ -30,7 +30,14 @@ static int launch_bn(mrcnn_ctx* ctx, const ConvPlan& plan) {
     attr_done = true;
   }
   ProfScope ps(ctx, PROF_CONV_GEMM, plan.flops);
-  conv_gemm_kernel<BN><<<plan.grid, CG_THREADS, cg::Cfg<BN>::kSmemBytes, ctx->stream>>>(plan.tmA, plan.tmB, plan.tmC, plan.tmR, plan.p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(plan.grid); cfg.blockDim = dim3(CG_THREADS);
+  cfg.dynamicSmemBytes = cg::Cfg<BN>::kSmemBytes; cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // PDL: see griddepcontrol.wait in the kernel
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  MRCNN_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN>, plan.tmA, plan.tmB, plan.tmC, plan.tmR, plan.p));
   MRCNN_LAUNCH_CHECK(ctx);
   return MRCNN_OK;
 }

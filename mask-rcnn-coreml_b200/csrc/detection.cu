@@ -73,13 +73,9 @@ det_finalize_kernel(const float4* __restrict__ fbox, const float* __restrict__ f
   extern __shared__ unsigned long long smem_u64[];
   const int img = blockIdx.x, tid = threadIdx.x;
   const int K = fcount[img];
-  NmsResolveSmem s;
-  s.remv = smem_u64;
-  s.diag = smem_u64 + words;
-  int* ip = (int*)(s.diag + NMS_TILE);
-  s.kept_rows = ip;
-  s.misc = ip + NMS_TILE;
-  s.class_count = s.misc + 4;
+  int* rest = nullptr;
+  NmsResolveSmem s = nms_resolve_carve(smem_u64, words, &rest);
+  s.class_count = rest;
   int* kept = s.class_count + ncls_cap;   // [R]
   float* kscore = (float*)(kept + R);     // [R]
   float* kcls = kscore + R;               // [R]
@@ -162,8 +158,7 @@ int detection_run(mrcnn_ctx* ctx, int batch, int64_t R64, const float* d_rois, c
                                              cfg.detection_nms_iou, ctx->d_dmask);
   MRCNN_LAUNCH_CHECK(ctx);
   const int ncls_cap = cfg.num_classes;
-  size_t sm = sizeof(unsigned long long) * (words + NMS_TILE) +
-              sizeof(int) * (NMS_TILE + 4 + ncls_cap + R) + sizeof(float) * 2 * R;
+  size_t sm = nms_resolve_smem_bytes(words) + sizeof(int) * (ncls_cap + R) + sizeof(float) * 2 * R;
   MRCNN_REQUIRE(ctx, sm <= 200 * 1024, "detection: workspace exceeds shared memory");
   if (sm > 48 * 1024) {
     MRCNN_CUDA_TRY(ctx, cudaFuncSetAttribute(det_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

@@ -50,18 +50,43 @@ nms_mask_kernel(const float4* __restrict__ boxes, const float* __restrict__ cls,
   mask[((size_t)img * stride_boxes + i) * words + cb] = bits;
 }
 
-// Sequential resolution, executed by one CTA (blockDim.x >= 64, multiple of 32).
-// shared scratch supplied by the caller:
-//   remv[words], diag[64], kept_rows[64], s_misc[4], class_count[ncls_cap] (if cls)
-// Returns (in every thread) the number of kept boxes; kept indices are appended
-// to kept_out (shared or global) in visiting order.
+// Sequential resolution, executed by one CTA (blockDim.x >= 256, multiple of 32).  Boxes are visited in
+// super-chunks of NMS_SUPER mask words (256 boxes): everything the order-dependent walk needs (the intra-chunk
+// block of the bitmask, selectability bits, classes) is first staged in shared memory by all threads, one thread
+// then walks the alive candidates touching shared memory only, and all threads OR the kept rows into the removal
+// words of the later chunks.  Returns (in every thread) the number of kept boxes; kept indices are appended to
+// kept_out (shared or global) in visiting order.
+#define NMS_SUPER 4
+#define NMS_SUPER_BOXES (NMS_SUPER * NMS_TILE)
+
 struct NmsResolveSmem {
   unsigned long long* remv;       // [words]
-  unsigned long long* diag;       // [64]
-  int* kept_rows;                 // [64]
+  unsigned long long* diag;       // [NMS_SUPER_BOXES * NMS_SUPER]
+  unsigned long long* svalid;     // [NMS_SUPER]
+  float* scls;                    // [NMS_SUPER_BOXES]
+  int* kept_rows;                 // [NMS_SUPER_BOXES]
   int* misc;                      // [4]: 0 kept_total, 1 kept_in_chunk, 2 stop flag
   int* class_count;               // [ncls_cap] or nullptr
 };
+
+// bytes of shared memory nms_resolve needs (excluding class_count and the caller's kept list), 8-byte aligned
+__host__ __device__ inline size_t nms_resolve_smem_bytes(int words) {
+  return sizeof(unsigned long long) * (size_t)(words + NMS_SUPER_BOXES * NMS_SUPER + NMS_SUPER) +
+         sizeof(float) * NMS_SUPER_BOXES + sizeof(int) * (NMS_SUPER_BOXES + 4);
+}
+
+__device__ __forceinline__ NmsResolveSmem nms_resolve_carve(unsigned long long* base, int words, int** rest) {
+  NmsResolveSmem s;
+  s.remv = base;
+  s.diag = s.remv + words;
+  s.svalid = s.diag + NMS_SUPER_BOXES * NMS_SUPER;
+  s.scls = (float*)(s.svalid + NMS_SUPER);
+  s.kept_rows = (int*)(s.scls + NMS_SUPER_BOXES);
+  s.misc = s.kept_rows + NMS_SUPER_BOXES;
+  s.class_count = nullptr;
+  *rest = s.misc + 4;
+  return s;
+}
 
 __device__ __forceinline__ int nms_resolve(const float4* __restrict__ boxes,
                                            const float* __restrict__ cls,
@@ -70,52 +95,59 @@ __device__ __forceinline__ int nms_resolve(const float4* __restrict__ boxes,
                                            int max_per_class, int ncls_cap,
                                            NmsResolveSmem s, int* kept_out) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int nchunks = (n + NMS_TILE - 1) / NMS_TILE;
+  const int nchunks = (n + NMS_TILE - 1) / NMS_TILE;               // mask words in use
+  const int nsuper = (nchunks + NMS_SUPER - 1) / NMS_SUPER;
   for (int w = tid; w < words; w += nt) s.remv[w] = 0ull;
   if (s.class_count) for (int k = tid; k < ncls_cap; k += nt) s.class_count[k] = 0;
   if (tid == 0) { s.misc[0] = 0; s.misc[1] = 0; s.misc[2] = 0; }
   __syncthreads();
-  for (int c = 0; c < nchunks; ++c) {
-    const int row0 = c * NMS_TILE;
-    // step 1: diagonal words + selectability of the 64 rows of this chunk
-    unsigned long long my_valid = 0ull;
-    if (tid < NMS_TILE) {
-      int row = row0 + tid;
-      unsigned long long d = 0ull;
+  unsigned int* svalid32 = reinterpret_cast<unsigned int*>(s.svalid);
+  for (int c = 0; c < nsuper; ++c) {
+    const int row0 = c * NMS_SUPER_BOXES;
+    const int w0 = c * NMS_SUPER;
+    // step 1: stage the intra-chunk mask block, selectability and classes of the 256 rows of this super-chunk
+    if (tid < NMS_SUPER_BOXES) {
+      const int row = row0 + tid;
       bool ok = false;
-      if (row < n) {
-        d = mask[(size_t)row * words + c];
-        ok = box_selectable(boxes[row]);
+      float cv = 0.0f;
+      const int myw = tid / NMS_TILE;                                // word (within the super-chunk) this row lives in
+      #pragma unroll
+      for (int j = 0; j < NMS_SUPER; ++j) {
+        unsigned long long d = 0ull;
+        if (row < n && j >= myw && w0 + j < nchunks) d = mask[(size_t)row * words + w0 + j];   // only words >= the row's own were written
+        s.diag[tid * NMS_SUPER + j] = d;
       }
-      s.diag[tid] = d;
-      my_valid = ok ? 1ull : 0ull;
+      if (row < n) { ok = box_selectable(boxes[row]); if (cls) cv = cls[row]; }
+      s.scls[tid] = cv;
+      const unsigned int bal = __ballot_sync(0xffffffffu, ok);
+      if ((tid & 31) == 0) svalid32[tid >> 5] = bal;
     }
-    // ballot the valid bits of threads 0..63 (two warps) into one word
-    unsigned int bal = __ballot_sync(0xffffffffu, my_valid != 0ull);
-    if (tid == 0) s.kept_rows[0] = (int)bal;       // reuse as scratch (lo)
-    if (tid == 32) s.kept_rows[1] = (int)bal;      // (hi)
     __syncthreads();
-    // step 2: one thread walks the alive candidates of the chunk in order
+    // step 2: one thread walks the alive candidates in order (shared memory only)
     if (tid == 0) {
-      unsigned long long valid = ((unsigned long long)(unsigned int)s.kept_rows[1] << 32) |
-                                 (unsigned long long)(unsigned int)s.kept_rows[0];
-      unsigned long long alive = valid & ~s.remv[c];
+      unsigned long long alive[NMS_SUPER];
+      #pragma unroll
+      for (int j = 0; j < NMS_SUPER; ++j) alive[j] = (w0 + j < nchunks) ? (s.svalid[j] & ~s.remv[w0 + j]) : 0ull;
       int total = s.misc[0];
       int nk = 0;
-      while (alive && total < max_total) {
-        int t = __ffsll((long long)alive) - 1;
-        alive &= ~(1ull << t);
-        int row = row0 + t;
-        if (s.class_count) {
-          int k = (int)cls[row];
-          k = k < 0 ? 0 : (k >= ncls_cap ? ncls_cap - 1 : k);
-          if (s.class_count[k] >= max_per_class) continue;   // Utils.swift:192 per class call
-          s.class_count[k]++;
+      #pragma unroll
+      for (int j = 0; j < NMS_SUPER; ++j) {
+        while (alive[j] && total < max_total) {
+          const int t = __ffsll((long long)alive[j]) - 1;
+          alive[j] &= ~(1ull << t);
+          const int idx = j * NMS_TILE + t;
+          if (s.class_count) {
+            int k = (int)s.scls[idx];
+            k = k < 0 ? 0 : (k >= ncls_cap ? ncls_cap - 1 : k);
+            if (s.class_count[k] >= max_per_class) continue;     // Utils.swift:192 per class call
+            s.class_count[k]++;
+          }
+          #pragma unroll
+          for (int jj = 0; jj < NMS_SUPER; ++jj) if (jj >= j) alive[jj] &= ~s.diag[idx * NMS_SUPER + jj];
+          kept_out[total] = row0 + idx;
+          s.kept_rows[nk++] = row0 + idx;
+          total++;
         }
-        alive &= ~s.diag[t];
-        kept_out[total] = row;
-        s.kept_rows[nk++] = row;
-        total++;
       }
       s.misc[0] = total;
       s.misc[1] = nk;
@@ -125,13 +157,28 @@ __device__ __forceinline__ int nms_resolve(const float4* __restrict__ boxes,
     const int nk = s.misc[1];
     const int stop = s.misc[2];
     if (stop) break;
-    // step 3: OR the kept rows into the removal words of later chunks
-    if (nk > 0) {
-      for (int w = c + 1 + tid; w < nchunks; w += nt) {  // words >= nchunks; later words are never visited
-        unsigned long long acc = 0ull;
-        #pragma unroll 4
-        for (int k = 0; k < nk; ++k) acc |= mask[(size_t)s.kept_rows[k] * words + w];
-        s.remv[w] |= acc;
+    // step 3: OR the kept rows into the removal words of the later super-chunks.  (kept row, word) pairs are
+    // flattened over all threads: consecutive threads read consecutive words of one mask row (coalesced), every
+    // load is independent, and non-zero words are merged with shared-memory atomics.
+    const int wfirst = w0 + NMS_SUPER;
+    const int nlater = nchunks - wfirst;
+    if (nk > 0 && nlater > 0) {
+      const int pairs = nk * nlater;
+      for (int p0 = tid; p0 < pairs; p0 += 4 * nt) {
+        unsigned long long v[4];
+        int wv[4];
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int pp = p0 + u * nt;
+          v[u] = 0ull; wv[u] = wfirst;
+          if (pp < pairs) {
+            const int k = pp / nlater;
+            wv[u] = wfirst + (pp - k * nlater);
+            v[u] = mask[(size_t)s.kept_rows[k] * words + wv[u]];
+          }
+        }
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) if (v[u]) atomicOr(&s.remv[wv[u]], v[u]);
       }
     }
     __syncthreads();

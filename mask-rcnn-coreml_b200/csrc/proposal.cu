@@ -209,21 +209,15 @@ sort_decode_kernel(const unsigned long long* __restrict__ cand, int cand_stride,
 }
 
 // One CTA per image: sequential NMS resolve + output (ProposalLayer.swift:169-192).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 proposal_resolve_kernel(const float4* __restrict__ sboxes, const int32_t* __restrict__ sorder,
                         const unsigned long long* __restrict__ mask, int n, int stride, int words,
                         int max_proposals, float4* __restrict__ rois_out,
                         int32_t* __restrict__ keep_anchor, int32_t* __restrict__ count_out) {
   extern __shared__ unsigned long long smem_u64[];
   const int img = blockIdx.x;
-  NmsResolveSmem s;
-  s.remv = smem_u64;
-  s.diag = smem_u64 + words;
-  int* ip = (int*)(s.diag + NMS_TILE);
-  s.kept_rows = ip;
-  s.misc = ip + NMS_TILE;
-  s.class_count = nullptr;
-  int* kept = s.misc + 4;               // [max_proposals]
+  int* kept = nullptr;                  // [max_proposals]
+  NmsResolveSmem s = nms_resolve_carve(smem_u64, words, &kept);
   const float4* b = sboxes + (size_t)img * stride;
   const unsigned long long* mk = mask + (size_t)img * stride * words;
   int cnt = nms_resolve(b, nullptr, mk, n, words, max_proposals, 0, 0, s, kept);
@@ -333,8 +327,8 @@ int proposal_run(mrcnn_ctx* ctx, int batch, int64_t N, const float* d_probs, con
   MRCNN_LAUNCH_CHECK(ctx);
   }
   ProfScope ps2(ctx, PROF_NMS_RESOLVE, (double)batch * (cfg.max_proposals * 8.0 * words + cfg.max_proposals * 20.0));
-  size_t rs = sizeof(unsigned long long) * (words + NMS_TILE) + sizeof(int) * (NMS_TILE + 4 + cfg.max_proposals);
-  proposal_resolve_kernel<<<batch, 256, rs, s>>>(ctx->d_sboxes, ctx->d_sorder, ctx->d_mask, pre, stride,
+  size_t rs = nms_resolve_smem_bytes(words) + sizeof(int) * cfg.max_proposals;
+  proposal_resolve_kernel<<<batch, 1024, rs, s>>>(ctx->d_sboxes, ctx->d_sorder, ctx->d_mask, pre, stride,
                                                  words, cfg.max_proposals, (float4*)d_rois_out,
                                                  d_keep_anchor, d_count);
   MRCNN_LAUNCH_CHECK(ctx);
