@@ -37,6 +37,15 @@ IMG = 1024
 
 
 # --------------------------------------------------------------------------- utils
+def load_traffic(kernel_class):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch for a kernel class, from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    try:
+        return json.load(open(p))[kernel_class]["traffic_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -340,15 +349,15 @@ class PipelineWorkload:
         peak = peaks["bf16_sustained"]
         return {"kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM convolution, every dense layer)", "bound": "tensor",
                 "achieved": ach, "peak": peak, "peak_source": peaks["source"] + " (sustained cuBLAS bf16; fp16 runs at the same rate)",
-                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "launches": n, "avg_launch_ms": ms / max(n, 1),
-                "algorithmic_flops_per_launch": work / max(n, 1)}
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": load_traffic("conv_gemm_tcgen05"), "traffic_unit": "B/launch (ncu dram bytes, profiles/traffic_r1.json)",
+                "launches": n, "avg_launch_ms": ms / max(n, 1), "algorithmic_flops_per_launch": work / max(n, 1)}
 
     def extra_rooflines(self, prof, peaks):
         ms, n, work = prof["roialign"]
         ach = work / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         return {"roofline_roialign": {"kernel": "roialign_nhwc_kernel (pool 7 + pool 14)", "bound": "hbm", "achieved": ach,
-                                      "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None,
-                                      "launches": n, "avg_launch_ms": ms / max(n, 1)},
+                                      "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": load_traffic("roialign"),
+                                      "launches": n, "avg_launch_ms": ms / max(n, 1), "algorithmic_bytes_per_launch": work / max(n, 1)},
                 "stage_ms": dict(self.ctx.stage_times())}
 
     def cpu_baseline(self):

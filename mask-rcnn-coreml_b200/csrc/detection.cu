@@ -110,6 +110,99 @@ det_finalize_kernel(const float4* __restrict__ fbox, const float* __restrict__ f
   if (count_out && tid == 0) count_out[img] = nk < max_det ? nk : max_det;
 }
 
+// Per-class NMS is independent per class (the bitmask only links same-class pairs), so the order-dependent walk
+// is done by one thread PER CLASS in parallel: class k's thread visits its candidates in roi order, keeps at most
+// max_det of them and ORs the kept rows into its private removal words.  Then the kept set is compacted and ranked
+// exactly like det_finalize_kernel does (the final order does not depend on the order of the kept list).
+__global__ void __launch_bounds__(DET_THREADS)
+det_finalize_percls_kernel(const float4* __restrict__ fbox, const float* __restrict__ fcls,
+                           const float* __restrict__ fscore, const int32_t* __restrict__ fidx,
+                           const int32_t* __restrict__ fcount, const unsigned long long* __restrict__ mask,
+                           int R, int words, int max_det, int ncls_cap, float* __restrict__ out,
+                           int32_t* __restrict__ keep_roi, int32_t* __restrict__ count_out) {
+  extern __shared__ unsigned long long smem_u64[];
+  const int img = blockIdx.x, tid = threadIdx.x;
+  const int K = fcount[img];
+  const int nwords = (K + 63) >> 6;
+  unsigned long long* cbits = smem_u64;                              // [ncls][words] candidates of each class
+  unsigned long long* rem = cbits + (size_t)ncls_cap * words;        // [ncls][words] suppressed by a kept box of that class
+  unsigned long long* valid = rem + (size_t)ncls_cap * words;        // [words] selectable (Utils.swift:195)
+  unsigned long long* keptbits = valid + words;                      // [words]
+  int* kept = (int*)(keptbits + words);                              // [R]
+  float* kscore = (float*)(kept + R);                                // [R]
+  float* kcls = kscore + R;                                          // [R]
+  int* counter = (int*)(kcls + R);
+  unsigned long long* smask = (unsigned long long*)(((uintptr_t)(counter + 1) + 7) & ~(uintptr_t)7);   // [K][nwords] staged bitmask rows
+  const float4* b = fbox + (size_t)img * R;
+  const float* c = fcls + (size_t)img * R;
+  const float* sc = fscore + (size_t)img * R;
+  const unsigned long long* mk = mask + (size_t)img * R * words;
+  for (int i = tid; i < 2 * ncls_cap * words + 2 * words; i += DET_THREADS) smem_u64[i] = 0ull;
+  if (tid == 0) *counter = 0;
+  // stage the (upper-triangular) bitmask rows of the K candidates: the per-class walks then touch shared memory only
+  for (int e = tid; e < K * nwords; e += DET_THREADS) {
+    const int i = e / nwords, w = e - i * nwords;
+    smask[e] = (w >= (i >> 6)) ? mk[(size_t)i * words + w] : 0ull;
+  }
+  __syncthreads();
+  for (int i = tid; i < K; i += DET_THREADS) {
+    int k = (int)c[i];
+    k = k < 0 ? 0 : (k >= ncls_cap ? ncls_cap - 1 : k);
+    const unsigned long long bit = 1ull << (i & 63);
+    atomicOr(&cbits[(size_t)k * words + (i >> 6)], bit);
+    if (box_selectable(b[i])) atomicOr(&valid[i >> 6], bit);
+  }
+  __syncthreads();
+  if (tid < ncls_cap) {
+    const unsigned long long* cb = cbits + (size_t)tid * words;
+    unsigned long long* rm = rem + (size_t)tid * words;
+    int count = 0;
+    for (int w = 0; w < nwords && count < max_det; ++w) {
+      unsigned long long alive = cb[w] & valid[w] & ~rm[w];
+      while (alive && count < max_det) {                  // Utils.swift:192: at most max per class call
+        const int t = __ffsll((long long)alive) - 1;
+        const unsigned long long bit = 1ull << t;
+        alive &= ~bit;
+        const int i = (w << 6) + t;
+        atomicOr(&keptbits[w], bit);
+        ++count;
+        const unsigned long long* row = smask + (size_t)i * nwords;
+        alive &= ~row[w];
+        for (int ww = w + 1; ww < nwords; ++ww) rm[ww] |= row[ww];
+      }
+    }
+  }
+  // zero the whole output first (rows >= count must be zero, DetectionLayer.swift:228-231)
+  for (int i = tid; i < max_det * 6; i += DET_THREADS) out[(size_t)img * max_det * 6 + i] = 0.0f;
+  if (keep_roi) for (int i = tid; i < max_det; i += DET_THREADS) keep_roi[(size_t)img * max_det + i] = -1;
+  __syncthreads();
+  for (int i = tid; i < K; i += DET_THREADS)
+    if ((keptbits[i >> 6] >> (i & 63)) & 1ull) {
+      const int slot = atomicAdd(counter, 1);
+      kept[slot] = i; kscore[slot] = sc[i]; kcls[slot] = c[i];
+    }
+  __syncthreads();
+  const int nk = *counter;
+  // rank of every kept element in the order (score desc, class asc, position asc)
+  for (int e = tid; e < nk; e += DET_THREADS) {
+    const float se = kscore[e], ce = kcls[e];
+    const int pe = kept[e];
+    int rank = 0;
+    for (int f = 0; f < nk; ++f) {
+      const float sf = kscore[f], cf = kcls[f];
+      const int pf = kept[f];
+      rank += ((sf > se) || (sf == se && (cf < ce || (cf == ce && pf < pe)))) ? 1 : 0;
+    }
+    if (rank < max_det) {
+      const float4 box = b[pe];
+      float* o = out + ((size_t)img * max_det + rank) * 6;
+      o[0] = box.x; o[1] = box.y; o[2] = box.z; o[3] = box.w; o[4] = ce; o[5] = se;
+      if (keep_roi) keep_roi[(size_t)img * max_det + rank] = fidx[(size_t)img * R + pe];
+    }
+  }
+  if (count_out && tid == 0) count_out[img] = nk < max_det ? nk : max_det;
+}
+
 static int detection_ensure_ws(mrcnn_ctx* ctx, int batch, int64_t R) {
   if (batch <= ctx->det_batch && R <= ctx->det_rois) return MRCNN_OK;
   MRCNN_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -158,14 +251,25 @@ int detection_run(mrcnn_ctx* ctx, int batch, int64_t R64, const float* d_rois, c
                                              cfg.detection_nms_iou, ctx->d_dmask);
   MRCNN_LAUNCH_CHECK(ctx);
   const int ncls_cap = cfg.num_classes;
-  size_t sm = nms_resolve_smem_bytes(words) + sizeof(int) * (ncls_cap + R) + sizeof(float) * 2 * R;
-  MRCNN_REQUIRE(ctx, sm <= 200 * 1024, "detection: workspace exceeds shared memory");
-  if (sm > 48 * 1024) {
-    MRCNN_CUDA_TRY(ctx, cudaFuncSetAttribute(det_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  // per-class parallel resolve when its bitmaps fit in shared memory, else the generic sequential resolve
+  const size_t sm_pc = sizeof(unsigned long long) * (2 * (size_t)ncls_cap * words + 2 * words) + sizeof(int) * (R + 1) + sizeof(float) * 2 * R +
+                       16 + sizeof(unsigned long long) * (size_t)R * words;
+  if (sm_pc <= 200 * 1024 && ncls_cap <= DET_THREADS) {
+    if (sm_pc > 48 * 1024)
+      MRCNN_CUDA_TRY(ctx, cudaFuncSetAttribute(det_finalize_percls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pc));
+    det_finalize_percls_kernel<<<batch, DET_THREADS, sm_pc, s>>>(ctx->d_fbox, ctx->d_fcls, ctx->d_fscore, ctx->d_fidx,
+                                                                 ctx->d_fcount, ctx->d_dmask, R, words, cfg.max_detections,
+                                                                 ncls_cap, d_out, d_keep_roi, d_count);
+  } else {
+    size_t sm = nms_resolve_smem_bytes(words) + sizeof(int) * (ncls_cap + R) + sizeof(float) * 2 * R;
+    MRCNN_REQUIRE(ctx, sm <= 200 * 1024, "detection: workspace exceeds shared memory");
+    if (sm > 48 * 1024) {
+      MRCNN_CUDA_TRY(ctx, cudaFuncSetAttribute(det_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    }
+    det_finalize_kernel<<<batch, DET_THREADS, sm, s>>>(ctx->d_fbox, ctx->d_fcls, ctx->d_fscore, ctx->d_fidx,
+                                                       ctx->d_fcount, ctx->d_dmask, R, words, cfg.max_detections,
+                                                       ncls_cap, d_out, d_keep_roi, d_count);
   }
-  det_finalize_kernel<<<batch, DET_THREADS, sm, s>>>(ctx->d_fbox, ctx->d_fcls, ctx->d_fscore, ctx->d_fidx,
-                                                     ctx->d_fcount, ctx->d_dmask, R, words, cfg.max_detections,
-                                                     ncls_cap, d_out, d_keep_roi, d_count);
   MRCNN_LAUNCH_CHECK(ctx);
   return MRCNN_OK;
 }

@@ -101,11 +101,26 @@ roialign_chw_kernel(const float* __restrict__ rois, int roi_stride, int R, Pyram
   }
 }
 
-// v0 NHWC fp16: one CTA per roi, one warp per sample, 8 channels (16 B) per lane
-// per step -> every tap is a contiguous C*2-byte run.
-__global__ void __launch_bounds__(256)
+// NHWC fp16: one CTA per roi.  The 2P axis samples (tap rows / columns and lerp weights) are computed once per
+// CTA into shared memory; then one warp per output sample, 8 channels (16 B) per lane per step, so every tap is a
+// contiguous C*2-byte run.  Two samples are in flight per warp iteration (8 independent 16-byte loads per lane).
+__device__ __forceinline__ uint32_t bilerp2(uint32_t a, uint32_t b, uint32_t c, uint32_t d, float lx, float ly) {
+  const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&a)), fb = __half22float2(*reinterpret_cast<const __half2*>(&b));
+  const float2 fc = __half22float2(*reinterpret_cast<const __half2*>(&c)), fd = __half22float2(*reinterpret_cast<const __half2*>(&d));
+  const __half2 r = __floats2half2_rn(bilerp(fa.x, fb.x, fc.x, fd.x, lx, ly), bilerp(fa.y, fb.y, fc.y, fd.y, lx, ly));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+__device__ __forceinline__ uint4 bilerp8(uint4 a, uint4 b, uint4 c, uint4 d, float lx, float ly) {
+  return make_uint4(bilerp2(a.x, b.x, c.x, d.x, lx, ly), bilerp2(a.y, b.y, c.y, d.y, lx, ly),
+                    bilerp2(a.z, b.z, c.z, d.z, lx, ly), bilerp2(a.w, b.w, c.w, d.w, lx, ly));
+}
+
+__global__ void __launch_bounds__(256, 3)
 roialign_nhwc_kernel(const float* __restrict__ rois, int roi_stride, int R, PyramidF16 pyr, int C, int P,
                      const int32_t* __restrict__ level, __half* __restrict__ out) {
+  __shared__ int s_lo[2][64], s_hi[2][64];        // [0] = y axis, [1] = x axis; lo = -1 marks an out-of-range sample
+  __shared__ float s_lerp[2][64];
   const int img = blockIdx.y, r = blockIdx.x;
   const int64_t ri = (int64_t)img * R + r;
   const int PP = P * P;
@@ -121,38 +136,42 @@ roialign_nhwc_kernel(const float* __restrict__ rois, int roi_stride, int R, Pyra
   const int m = lv - 2;
   const int H = pyr.h[m], W = pyr.w[m];
   const __half* fm = pyr.p[m] + (size_t)img * H * W * C;
-  const float* rr = rois + ri * roi_stride;
-  const float y1 = rr[0], x1 = rr[1], y2 = rr[2], x2 = rr[3];
-  for (int sidx = wid; sidx < PP; sidx += nw) {
-    int py = sidx / P, px = sidx - py * P;
-    SampleAxis sy = sample_axis(y1, y2, H, P, py);
-    SampleAxis sx = sample_axis(x1, x2, W, P, px);
-    uint4* dst = reinterpret_cast<uint4*>(o + (size_t)sidx * C);
-    if (!(sy.ok && sx.ok)) {
-      for (int v = lane; v < cvec; v += 32) dst[v] = make_uint4(0, 0, 0, 0);
-      continue;
+  if (threadIdx.x < 128) {
+    const int axis = threadIdx.x >> 6, i = threadIdx.x & 63;
+    if (i < P) {
+      const float* rr = rois + ri * roi_stride;
+      const SampleAxis sa = axis == 0 ? sample_axis(rr[0], rr[2], H, P, i) : sample_axis(rr[1], rr[3], W, P, i);
+      s_lo[axis][i] = sa.ok ? sa.lo : -1; s_hi[axis][i] = sa.hi; s_lerp[axis][i] = sa.lerp;
     }
-    const uint4* ptl = reinterpret_cast<const uint4*>(fm + ((size_t)sy.lo * W + sx.lo) * C);
-    const uint4* ptr = reinterpret_cast<const uint4*>(fm + ((size_t)sy.lo * W + sx.hi) * C);
-    const uint4* pbl = reinterpret_cast<const uint4*>(fm + ((size_t)sy.hi * W + sx.lo) * C);
-    const uint4* pbr = reinterpret_cast<const uint4*>(fm + ((size_t)sy.hi * W + sx.hi) * C);
+  }
+  __syncthreads();
+  for (int s0 = wid; s0 < PP; s0 += 2 * nw) {
+    const int s1 = s0 + nw;
+    const bool has1 = s1 < PP;
+    const int py0 = s0 / P, px0 = s0 - py0 * P;
+    const int py1 = has1 ? s1 / P : py0, px1 = has1 ? s1 - py1 * P : px0;
+    const int yl0 = s_lo[0][py0], yh0 = s_hi[0][py0], xl0 = s_lo[1][px0], xh0 = s_hi[1][px0];
+    const int yl1 = s_lo[0][py1], yh1 = s_hi[0][py1], xl1 = s_lo[1][px1], xh1 = s_hi[1][px1];
+    const bool ok0 = (yl0 >= 0) && (xl0 >= 0), ok1 = has1 && (yl1 >= 0) && (xl1 >= 0);
     for (int v = lane; v < cvec; v += 32) {
-      uint4 a = __ldg(ptl + v), b = __ldg(ptr + v), c = __ldg(pbl + v), d = __ldg(pbr + v);
-      const __half2* ha = reinterpret_cast<const __half2*>(&a);
-      const __half2* hb = reinterpret_cast<const __half2*>(&b);
-      const __half2* hc = reinterpret_cast<const __half2*>(&c);
-      const __half2* hd = reinterpret_cast<const __half2*>(&d);
-      uint4 res;
-      __half2* hr = reinterpret_cast<__half2*>(&res);
-      #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float2 fa = __half22float2(ha[q]), fb = __half22float2(hb[q]);
-        float2 fc = __half22float2(hc[q]), fd = __half22float2(hd[q]);
-        float r0 = bilerp(fa.x, fb.x, fc.x, fd.x, sx.lerp, sy.lerp);
-        float r1 = bilerp(fa.y, fb.y, fc.y, fd.y, sx.lerp, sy.lerp);
-        hr[q] = __floats2half2_rn(r0, r1);
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      uint4 a0 = z, b0 = z, c0 = z, d0 = z, a1 = z, b1 = z, c1 = z, d1 = z;
+      if (ok0) {
+        a0 = __ldg(reinterpret_cast<const uint4*>(fm + ((size_t)yl0 * W + xl0) * C) + v);
+        b0 = __ldg(reinterpret_cast<const uint4*>(fm + ((size_t)yl0 * W + xh0) * C) + v);
+        c0 = __ldg(reinterpret_cast<const uint4*>(fm + ((size_t)yh0 * W + xl0) * C) + v);
+        d0 = __ldg(reinterpret_cast<const uint4*>(fm + ((size_t)yh0 * W + xh0) * C) + v);
       }
-      dst[v] = res;
+      if (ok1) {
+        a1 = __ldg(reinterpret_cast<const uint4*>(fm + ((size_t)yl1 * W + xl1) * C) + v);
+        b1 = __ldg(reinterpret_cast<const uint4*>(fm + ((size_t)yl1 * W + xh1) * C) + v);
+        c1 = __ldg(reinterpret_cast<const uint4*>(fm + ((size_t)yh1 * W + xl1) * C) + v);
+        d1 = __ldg(reinterpret_cast<const uint4*>(fm + ((size_t)yh1 * W + xh1) * C) + v);
+      }
+      // out-of-range samples are exactly zero (extrapolation value), in-range ones follow the oracle's op order
+      reinterpret_cast<uint4*>(o + (size_t)s0 * C)[v] = ok0 ? bilerp8(a0, b0, c0, d0, s_lerp[1][px0], s_lerp[0][py0]) : z;
+      if (has1)
+        reinterpret_cast<uint4*>(o + (size_t)s1 * C)[v] = ok1 ? bilerp8(a1, b1, c1, d1, s_lerp[1][px1], s_lerp[0][py1]) : z;
     }
   }
 }
