@@ -455,8 +455,8 @@ def run_ours(args):
                         "l2_policy": "per-step working set (batch activations + feature maps, > 1 GB) exceeds the 126 MB L2; no explicit flush"},
                        **getattr(wl, "config_extra", {})),
         "clocks": clocks,
-        "e2e": {"value": imgs / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": wl.h2d,
-                "d2h_bytes_per_step": wl.d2h},
+        "e2e": {"value": imgs / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": wl.h2d * world,
+                "d2h_bytes_per_step": wl.d2h * world},
         "gpu_launches": launches * args.steps,
         "roofline": wl.roofline(prof, peaks),
         "kernel_classes": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps,

@@ -28,23 +28,33 @@ nms_mask_kernel(const float4* __restrict__ boxes, const float* __restrict__ cls,
   const float* c = cls ? cls + (size_t)img * stride_boxes : nullptr;
 
   __shared__ RectD col_rect[NMS_TILE];
+  __shared__ float4 col_f[NMS_TILE];      // (x1, y1, ub(maxx), ub(maxy)) in fp32, upper bounds rounded up
   __shared__ float col_cls[NMS_TILE];
   const int t = threadIdx.x;
   const int cj = cb * NMS_TILE + t;
   if (cj < n) {
-    col_rect[t] = make_rect(b[cj]);
+    const RectD rc = make_rect(b[cj]);
+    col_rect[t] = rc;
+    col_f[t] = make_float4(b[cj].y, b[cj].x, __double2float_ru(rc.maxx), __double2float_ru(rc.maxy));
     col_cls[t] = c ? c[cj] : 0.0f;
   }
   __syncthreads();
   const int i = rb * NMS_TILE + t;
   if (i >= n) return;
   const RectD me = make_rect(b[i]);
+  const float mx1 = b[i].y, my1 = b[i].x;
+  const float mubx = __double2float_ru(me.maxx), muby = __double2float_ru(me.maxy);
   const float mycls = c ? c[i] : 0.0f;
   const int ncol = min(NMS_TILE, n - cb * NMS_TILE);
+  const bool prefilter = thr >= 0.0f;     // IoU of a disjoint pair is exactly 0, never > a non-negative threshold
   unsigned long long bits = 0ull;
   const int j0 = (cb == rb) ? t + 1 : 0;
   for (int j = j0; j < ncol; ++j) {
     if (c && col_cls[j] != mycls) continue;
+    // fp32 pre-test with conservative bounds: ub >= max edge exactly, so "ub <= other's min edge" proves the boxes
+    // do not overlap (intersection width or height <= 0 -> IoU 0 in the exact fp64 formula as well)
+    const float4 cf = col_f[j];
+    if (prefilter && ((cf.z <= mx1) || (mubx <= cf.x) || (cf.w <= my1) || (muby <= cf.y))) continue;
     if (iou_rect(col_rect[j], me) > thr) bits |= (1ull << j);
   }
   mask[((size_t)img * stride_boxes + i) * words + cb] = bits;
