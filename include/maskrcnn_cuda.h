@@ -223,6 +223,18 @@ MRCNN_API int mrcnn_detections_decode(mrcnn_ctx* ctx, int batch, const float* de
                             int32_t* class_out, double* score_out,
                             uint8_t* mask_u8_out);
 
+/* ---- Pre-processing in front of the path: Vision's `.scaleFit` (EvaluateCommand.swift:157,
+ * ViewController.swift:42).  Geometry as the reference's own letter-boxing (DetectionRenderer.swift:63-75): scale to
+ * fit, centred padding (black); bilinear, half-pixel centres.
+ *   src [src_h, src_w, 3] u8 -> dst [image_h, image_w, 3] u8 (ready for mrcnn_predict). */
+MRCNN_API int mrcnn_letterbox_eval(mrcnn_ctx* ctx, const uint8_t* src, int src_h, int src_w, uint8_t* dst);
+/* out5 = {scale, new_w, new_h, pad_x, pad_y} of that mapping (host arithmetic, no GPU needed). */
+MRCNN_API int mrcnn_letterbox_geometry(int src_h, int src_w, int dst_h, int dst_w, double out5[5]);
+/* Inverse mapping for results: boxes (y1,x1,y2,x2) normalised to the model frame -> normalised to the source
+ * image; rows of row_stride floats (4 for rois, 6 for detections), extra columns are copied.  Host arithmetic. */
+MRCNN_API int mrcnn_unletterbox_boxes(int src_h, int src_w, int dst_h, int dst_w, const float* boxes,
+                            int64_t n, int row_stride, float* out);
+
 /* ---- Multi-GPU: images shard across ranks, one all-gather of the packed
  * (detections | masks) rows.  The reference is single-process
  * (EvaluateCommand.swift:166-194 loops images serially); this is the only

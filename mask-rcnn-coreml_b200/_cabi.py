@@ -65,6 +65,9 @@ SIGNATURES = {
     "mrcnn_mask_eval": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
     "mrcnn_predict": (_i, [_vp, _i, _vp, _vp, _vp]),
     "mrcnn_detections_decode": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mrcnn_letterbox_eval": (_i, [_vp, _vp, _i, _i, _vp]),
+    "mrcnn_letterbox_geometry": (_i, [_i, _i, _i, _i, C.POINTER(C.c_double)]),
+    "mrcnn_unletterbox_boxes": (_i, [_i, _i, _i, _i, _vp, _i64, _i, _vp]),
     "mrcnn_nccl_unique_id": (_i, [_vp]),
     "mrcnn_comm_init": (_i, [_vp, _vp, _i, _i]),
     "mrcnn_predict_allgather": (_i, [_vp, _i, _vp, _vp, _vp]),

@@ -120,6 +120,22 @@ class MaskRCNN:
         out = self.prediction(image)
         return Detection.detectionsFromFeatureValue(out["detections"], out["mask"], context=self.ctx)
 
+    def letterbox(self, image, out=None):
+        """Vision's .scaleFit in front of the model (EvaluateCommand.swift:157): (H,W,3) u8 of any size -> model-sized image."""
+        h, w = image.shape[:2]
+        if out is None:
+            out = np.empty(self.shape, np.uint8)
+        check(self.ctx.handle, lib().mrcnn_letterbox_eval(self.ctx.handle, ptr(image), h, w, ptr(out)))
+        return out
+
+    def unletterbox(self, rows, src_h, src_w):
+        """(n, 4|6) rows with boxes normalised to the model frame -> normalised to the source image."""
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        out = np.empty_like(rows)
+        st = lib().mrcnn_unletterbox_boxes(src_h, src_w, self.shape[0], self.shape[1], ptr(rows), rows.shape[0], rows.shape[1], ptr(out))
+        check(self.ctx.handle, st)
+        return out
+
     def close(self):
         self.ctx.close()
 

@@ -555,3 +555,39 @@ ORC_API void orc_pyramid_roialign_nhwc_f16(const float* rois, int roi_stride, in
   if (level_out) memcpy(level_out, lv, sizeof(int) * (size_t)R);
   free(lv);
 }
+
+/* ------------------------------------------------------------------------- */
+/* Letter-boxing in front of the path (Vision .scaleFit, EvaluateCommand.swift:157).  Geometry =                */
+/* DetectionRenderer.swift:63-75 (scale factor by fitsHorizontally, padding split evenly); bilinear with        */
+/* half-pixel centres (Vision's filter is closed: PARITY UNPINNED), fp64, black padding, round half up to u8.   */
+/* ------------------------------------------------------------------------- */
+ORC_API void orc_letterbox(const uint8_t* src, int src_h, int src_w, int dst_h, int dst_w, uint8_t* dst) {
+  double hs = (double)dst_w / (double)src_w, vs = (double)dst_h / (double)src_h;      /* :63-64 */
+  int fits_h = (double)src_h * hs <= (double)dst_h;                                   /* :66 */
+  double scale = fits_h ? hs : vs;                                                    /* :68 */
+  double new_w = (double)src_w * scale, new_h = (double)src_h * scale;                /* :70 */
+  double pad_x = ((double)dst_w - new_w) / 2.0, pad_y = ((double)dst_h - new_h) / 2.0;/* :72-75 */
+  for (int Y = 0; Y < dst_h; ++Y)
+    for (int X = 0; X < dst_w; ++X) {
+      uint8_t* o = dst + ((size_t)Y * dst_w + X) * 3;
+      double cx = ((double)X + 0.5) - pad_x, cy = ((double)Y + 0.5) - pad_y;
+      if (!(cx >= 0.0 && cx < new_w && cy >= 0.0 && cy < new_h)) { o[0] = o[1] = o[2] = 0; continue; }
+      double sx = cx / scale - 0.5, sy = cy / scale - 0.5;
+      if (sx < 0.0) sx = 0.0;
+      if (sx > (double)(src_w - 1)) sx = (double)(src_w - 1);
+      if (sy < 0.0) sy = 0.0;
+      if (sy > (double)(src_h - 1)) sy = (double)(src_h - 1);
+      int x0 = (int)floor(sx), y0 = (int)floor(sy);
+      int x1 = x0 + 1 < src_w ? x0 + 1 : x0, y1 = y0 + 1 < src_h ? y0 + 1 : y0;
+      double fx = sx - (double)x0, fy = sy - (double)y0;
+      for (int c = 0; c < 3; ++c) {
+        double tl = src[((size_t)y0 * src_w + x0) * 3 + c], tr = src[((size_t)y0 * src_w + x1) * 3 + c];
+        double bl = src[((size_t)y1 * src_w + x0) * 3 + c], br = src[((size_t)y1 * src_w + x1) * 3 + c];
+        double dt = tr - tl; double mt = dt * fx; double top = tl + mt;
+        double db = br - bl; double mb = db * fx; double bot = bl + mb;
+        double dv = bot - top; double mv = dv * fy; double v = top + mv;
+        double r = v + 0.5;
+        o[c] = (uint8_t)r;
+      }
+    }
+}

@@ -161,3 +161,10 @@ def detections_decode(det, masks=None):
     mu8 = np.zeros((dn, s * s), dtype=np.uint8) if masks is not None else None
     n = lib().orc_detections_decode(_p(d), _p(m), C.c_int(dn), C.c_int(s), _p(idx), _p(bbox), _p(cls), _p(score), _p(mu8))
     return n, idx, bbox, cls, score, mu8
+
+
+def letterbox(src, dst_h=1024, dst_w=1024):
+    s = np.ascontiguousarray(src, dtype=np.uint8)
+    out = np.empty((dst_h, dst_w, 3), dtype=np.uint8)
+    lib().orc_letterbox(_p(s), C.c_int(s.shape[0]), C.c_int(s.shape[1]), C.c_int(dst_h), C.c_int(dst_w), _p(out))
+    return out

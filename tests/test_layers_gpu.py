@@ -229,3 +229,14 @@ def test_error_paths(pkg, ctx):
         pkg.ProposalLayer({"maxProposals": 5}, context=ctx)     # parameters must match the context
     with pytest.raises(pkg.MaskRCNNError):
         pkg.Context(anchors_path="/nonexistent/anchors.bin")
+
+
+def test_letterbox_matches_oracle(pkg, orc):
+    c = pkg.Context(image_h=256, image_w=256)
+    rng = np.random.default_rng(5)
+    for h, w in ((100, 180), (333, 211), (256, 256), (37, 500)):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        out = np.full((256, 256, 3), 7, np.uint8)
+        pkg._cabi.check(c.handle, pkg.lib().mrcnn_letterbox_eval(c.handle, pkg._cabi.ptr(img), h, w, pkg._cabi.ptr(out)))
+        np.testing.assert_array_equal(out, orc.letterbox(img, 256, 256))           # bit-exact (same fp64 op order)
+    c.close()

@@ -181,3 +181,30 @@ def test_proposal_small_end_to_end(orc):
     np.testing.assert_array_equal(keep, [0, 2, 5, -1, -1])
     np.testing.assert_array_equal(rois[:3], anchors[[0, 2, 5]])
     assert not rois[3:].any()
+
+
+def test_letterbox_known_answers(orc, pkg):
+    import ctypes as C
+    rng = np.random.default_rng(3)
+    # same size: identity
+    img = rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)
+    np.testing.assert_array_equal(orc.letterbox(img, 64, 64), img)
+    # 2:1 landscape into a square: scale = dst_w / src_w, rows padded evenly above and below (DetectionRenderer.swift:63-75)
+    img = np.full((32, 64, 3), 200, np.uint8)
+    out = orc.letterbox(img, 128, 128)
+    assert (out[:32] == 0).all() and (out[96:] == 0).all() and (out[32:96] == 200).all()
+    g = (C.c_double * 5)()
+    assert pkg.lib().mrcnn_letterbox_geometry(32, 64, 128, 128, g) == 0
+    assert list(g) == [2.0, 128.0, 64.0, 0.0, 32.0]
+    # portrait: columns padded
+    out = orc.letterbox(np.full((64, 32, 3), 9, np.uint8), 128, 128)
+    assert (out[:, :32] == 0).all() and (out[:, 96:] == 0).all() and (out[:, 32:96] == 9).all()
+    # exact 2x up-sampling of a horizontal ramp stays monotone and inside the source range
+    ramp = np.tile(np.arange(0, 64, dtype=np.uint8)[None, :, None] * 4, (64, 1, 3))
+    up = orc.letterbox(ramp, 128, 128)
+    assert (np.diff(up[5, :, 0].astype(int)) >= 0).all() and up.max() <= ramp.max()
+    # boxes map back: the full padded frame's image area becomes [0,1]
+    boxes = np.array([[0.25, 0.0, 0.75, 1.0, 3.0, 0.9]], np.float32)
+    back = np.zeros_like(boxes)
+    assert pkg.lib().mrcnn_unletterbox_boxes(32, 64, 128, 128, pkg._cabi.ptr(boxes), 1, 6, pkg._cabi.ptr(back)) == 0
+    np.testing.assert_allclose(back[0], [0, 0, 1, 1, 3, 0.9], atol=1e-6)
