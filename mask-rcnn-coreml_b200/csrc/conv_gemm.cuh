@@ -14,6 +14,13 @@
 //            loaded as 2-D TMA boxes (64, BN).
 //   K step = 64 channels of one tap (128 B rows, SWIZZLE_128B on both operands).
 //
+// Two launch shapes of the same kernel (template parameter CTAS):
+//   CTAS = 1  one CTA per SM, 128 x BN tiles, tcgen05.mma.cta_group::1
+//   CTAS = 2  thread-block clusters of two CTAs (one TPC): the pair computes a 256 x BN tile with
+//             tcgen05.mma.cta_group::2 issued by the leader CTA; each CTA stages its own 128 rows of A and HALF of the
+//             B tile (the tensor core reads both halves), which cuts the L2->smem operand traffic per flop by a third
+//             and makes the stages smaller, so the ring is deeper (6 instead of 4 stages at BN = 256).
+//
 // Persistent CTAs (one per SM), 6 warps:
 //   warp 0    TMA producer (one elected lane), NSTAGE-deep smem ring, mbarriers
 //   warp 1    tcgen05.mma issuer (one elected lane) + TMEM allocator
@@ -49,6 +56,7 @@ struct ConvGemmParams {
   int deconv_c;
   int tma_out;                 // 1: fp16 NHWC output staged in smem and written with TMA stores (cout % 64 == 0)
   int tma_res;                 // 1: residual (res_mode 1) tiles fetched with TMA into the same staging buffers
+  int ctas;                    // 1 or 2 (CTA pair / cta_group::2), must match the kernel instantiation and the cluster launch
   int nstages;                 // depth of the operand ring (A+B tiles), chosen per layer by the host
   int nbuf_log2;               // log2 of the number of 16 KB output / residual staging buffers (1 or 2)
   int maskdot;                 // 1: mask-head tail fused into the deconv epilogue (see epilogue_maskdot)
@@ -124,6 +132,71 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// ---- cluster / CTA-pair (cta_group::2) variants -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: data lands in this CTA's smem, the transaction bytes are signalled on the LEADER's barrier
+__device__ __forceinline__ void tma_load_4d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar,
+                                                 int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives (once the prior MMAs retire) on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+// The work items of one CTA: item w = first, first + step, ... < total.  An item is a 128 x BN tile (CTAS = 1) or the
+// 256 x BN tile of a CTA pair (CTAS = 2), of which this CTA owns the M tile 2 * (w / tiles_n) + crank.
+struct TileSched {
+  int first, step, total, ctas, crank;
+  __device__ __forceinline__ int count() const { return first < total ? (total - 1 - first) / step + 1 : 0; }
+  __device__ __forceinline__ void coords(const ConvGemmParams& p, int bn, int w, int& n0, int& x0, int& y0, int& img) const {
+    const int nt = w % p.tiles_n;
+    const int mt = (w / p.tiles_n) * ctas + crank;
+    n0 = nt * bn;
+    x0 = (mt % p.tiles_x) * p.tw;
+    y0 = ((mt / p.tiles_x) % p.tiles_y) * p.th;
+    img = mt / (p.tiles_x * p.tiles_y);       // == n_img for the phantom tile of an odd pair: TMA clips / zero-fills it
+  }
+};
+// accumulator-drained signal: local arrive (CTAS = 1) or arrive on the leader CTA's barrier (CTAS = 2)
+__device__ __forceinline__ void tempty_arrive(const TileSched& ts, uint32_t bar) {
+  if (ts.ctas == 2) mbar_arrive_cluster(mapa_rank(bar, 0)); else mbar_arrive(bar);
+}
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -180,21 +253,22 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BN> struct Cfg {
+template <int BN, int CTAS> struct Cfg {
   static constexpr int kABytes = CG_BM * CG_BK * 2;          // 16 KB
-  static constexpr int kBBytes = BN * CG_BK * 2;
+  static constexpr int kBBytes = (BN / CTAS) * CG_BK * 2;    // a CTA of a pair stages half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   // shared memory = operand ring (nstages x kStageBytes) + output/residual staging (nbuf x 16 KB) + barriers + bias
   // tile; the split between ring depth and staging depth is chosen per layer (host: conv_plan_build):
   //   compute-bound layers   deep ring,  2 staging buffers
   //   memory-bound layers    short ring, 4 staging buffers (residual prefetched 3 chunks ahead, 3 stores in flight)
-  static constexpr int kStagesDeep = (BN >= 256) ? 4 : ((BN >= 128) ? 6 : 8);
-  static constexpr int kStagesShort = (BN >= 256) ? 3 : ((BN >= 128) ? 5 : 6);
+  static constexpr int kStagesDeep = CTAS == 2 ? ((BN >= 256) ? 6 : 8) : ((BN >= 256) ? 4 : ((BN >= 128) ? 6 : 8));
+  static constexpr int kStagesShort = CTAS == 2 ? ((BN >= 256) ? 5 : ((BN >= 128) ? 6 : 8)) : ((BN >= 256) ? 3 : ((BN >= 128) ? 5 : 6));
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // BN in {32,64,128,256} -> power of two
   static constexpr int kOutStageBytes = CG_BM * 64 * 2;           // one 128-pixel x 64-channel fp16 sub-tile (SWIZZLE_128B)
   static constexpr int kMaxRingPlusOut = (kStagesDeep * kStageBytes + 2 * kOutStageBytes) > (kStagesShort * kStageBytes + 4 * kOutStageBytes)
                                              ? (kStagesDeep * kStageBytes + 2 * kOutStageBytes) : (kStagesShort * kStageBytes + 4 * kOutStageBytes);
   static constexpr int kSmemBytes = kMaxRingPlusOut + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias tile*/;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
 };
 
 // ---- staged epilogue (fp16 NHWC outputs): TMEM -> regs -> (+bias, +residual, ReLU) -> fp16 -> swizzled smem ->
@@ -206,7 +280,7 @@ template <int BN, int RES>
 __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, const CUtensorMap* tmC, const CUtensorMap* tmR,
                                                 uint8_t* out_gen, uint32_t out_base, float* bias_gen,
                                                 uint32_t rfull0, uint32_t tfull0, uint32_t tempty0,
-                                                uint32_t tmem_base, int total_tiles, int warp, int lane) {
+                                                uint32_t tmem_base, const TileSched ts, int warp, int lane) {
   constexpr int kStageBytes = CG_BM * 64 * 2;
   const uint32_t nb_log2 = (uint32_t)p.nbuf_log2, nb_mask = (1u << nb_log2) - 1u;
   const int q = warp & 3;
@@ -214,25 +288,16 @@ __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, const C
   const bool e0 = (threadIdx.x == 64);     // warp 2, lane 0: issues all bulk copies of this CTA's epilogue
   const int nchunks = (min(BN, p.cout) + 63) / 64;
   const float lo = p.relu ? 0.0f : -INFINITY;
-  auto tile_coords = [&](int tile, int& n0, int& x0, int& y0, int& img) {
-    const int nt = tile % p.tiles_n;
-    const int mt = tile / p.tiles_n;
-    n0 = nt * BN;
-    x0 = (mt % p.tiles_x) * p.tw;
-    y0 = ((mt / p.tiles_x) % p.tiles_y) * p.th;
-    img = mt / (p.tiles_x * p.tiles_y);
-  };
   uint32_t cc = 0;                         // chunk counter of this CTA (staging buffer = cc & nb_mask)
   int bias_n0 = -1;
   int acc = 0; uint32_t acc_phase = 0;
-  // residual prefetch (RES == 1): chunk j of this CTA = tile blockIdx.x + (j / nchunks) * gridDim.x, chunk j % nchunks
-  const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const uint32_t my_chunks = (uint32_t)(my_tiles * nchunks);
+  // residual prefetch (RES == 1): chunk j of this CTA = work item first + (j / nchunks) * step, chunk j % nchunks
+  const uint32_t my_chunks = (uint32_t)(ts.count() * nchunks);
   auto load_residual = [&](uint32_t j) {
     if (j >= my_chunks) return;
-    const int t = blockIdx.x + (int)(j / (uint32_t)nchunks) * gridDim.x;
+    const int t = ts.first + (int)(j / (uint32_t)nchunks) * ts.step;
     int n0, x0, y0, img;
-    tile_coords(t, n0, x0, y0, img);
+    ts.coords(p, BN, t, n0, x0, y0, img);
     const uint32_t b = j & nb_mask;
     mbar_expect_tx(rfull0 + 8u * b, (uint32_t)kStageBytes);
     tma_load_4d(out_base + b * (uint32_t)kStageBytes, tmR, rfull0 + 8u * b, n0 + (int)(j % (uint32_t)nchunks) * 64, x0, y0, img);
@@ -241,14 +306,15 @@ __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, const C
   if (RES == 1 && e0) for (uint32_t j = 0; j < nb_mask; ++j) load_residual(j);     // prefetch distance = nbuf - 1 chunks
   const uint32_t row_off = (uint32_t)row * 128u;
   const uint32_t sw = (uint32_t)(row & 7);
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  for (int tile = ts.first; tile < ts.total; tile += ts.step) {
     int n0, x0, y0, img;
-    tile_coords(tile, n0, x0, y0, img);
+    ts.coords(p, BN, tile, n0, x0, y0, img);
     const __half* res_row = p.residual;    // RES == 2: always a readable address (rows outside the map are clipped by the store)
     if (RES == 2) {
       int x = x0 + (row % p.tw), y = y0 + (row / p.tw);
       x = min(x, p.w_out - 1); y = min(y, p.h_out - 1);
-      res_row = p.residual + (((size_t)img * p.res_h + (y >> 1)) * (size_t)p.res_w + (x >> 1)) * (size_t)p.res_ld;
+      const int im = min(img, p.n_img - 1);
+      res_row = p.residual + (((size_t)im * p.res_h + (y >> 1)) * (size_t)p.res_w + (x >> 1)) * (size_t)p.res_ld;
     }
     if (n0 != bias_n0) {                   // stage this N tile's bias (zeros when there is none) in smem
       epi_bar_sync();
@@ -304,7 +370,7 @@ __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, const C
       if (c == nchunks - 1) {              // accumulator fully read: hand the TMEM stage back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+        if (lane == 0) tempty_arrive(ts, tempty0 + 8u * acc);
       }
       fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the bulk-copy engine
       epi_bar_sync();
@@ -334,21 +400,21 @@ __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, const C
 // deconvolution output itself is never written.  Invalid slots produce 0.
 template <int BN>
 __device__ __forceinline__ void epilogue_maskdot(const ConvGemmParams& p, float* bias_gen, uint32_t tfull0, uint32_t tempty0,
-                                                 uint32_t tmem_base, int total_tiles, int warp, int lane) {
+                                                 uint32_t tmem_base, const TileSched ts, int warp, int lane) {
   const int q = warp & 3;
   const int row = q * 32 + lane;
   float* w_gen = bias_gen + BN;
   float* out = reinterpret_cast<float*>(p.out);
   int acc = 0; uint32_t acc_phase = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    const int nt = tile % p.tiles_n;
-    const int mt = tile / p.tiles_n;
-    const int x = (mt % p.tiles_x) * p.tw + (row % p.tw);
-    const int y = ((mt / p.tiles_x) % p.tiles_y) * p.th + (row / p.tw);
-    const int img = mt / (p.tiles_x * p.tiles_y);
-    const bool pix_ok = (x < p.w_out) && (y < p.h_out);
-    const int valid = __ldg(p.md_valid + img);
-    int cls = __ldg(p.md_cls + img);
+  for (int tile = ts.first; tile < ts.total; tile += ts.step) {
+    int n0, x0, y0, img;
+    ts.coords(p, BN, tile, n0, x0, y0, img);
+    const int nt = n0 / BN;
+    const int x = x0 + (row % p.tw), y = y0 + (row / p.tw);
+    const bool pix_ok = (x < p.w_out) && (y < p.h_out) && (img < p.n_img);
+    const int im = min(img, p.n_img - 1);
+    const int valid = __ldg(p.md_valid + im);
+    int cls = __ldg(p.md_cls + im);
     cls = cls < 0 ? 0 : (cls >= p.md_ncls ? p.md_ncls - 1 : cls);
     epi_bar_sync();                        // everybody is done with the previous tile's bias / weight rows
     for (int i = threadIdx.x - 64; i < BN; i += 128) {
@@ -382,7 +448,7 @@ __device__ __forceinline__ void epilogue_maskdot(const ConvGemmParams& p, float*
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+    if (lane == 0) tempty_arrive(ts, tempty0 + 8u * acc);
     if (pix_ok) {
       const int dy = nt >> 1, dx = nt & 1;
       const float m = valid ? 1.0f / (1.0f + expf(-(dot + __ldg(p.md_b + cls)))) : 0.0f;
@@ -394,12 +460,12 @@ __device__ __forceinline__ void epilogue_maskdot(const ConvGemmParams& p, float*
 
 }  // namespace cg
 
-template <int BN>
+template <int BN, int CTAS>
 __global__ void __launch_bounds__(CG_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                  const __grid_constant__ ConvGemmParams p) {
-  using C = cg::Cfg<BN>;
+  using C = cg::Cfg<BN, CTAS>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-B aligned operand ring (SWIZZLE_128B requirement)
   const uint32_t smem_base = (cg::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -420,18 +486,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t crank = (CTAS == 2) ? cg::cluster_ctarank() : 0u;      // rank inside the CTA pair; 0 = leader (issues the MMAs)
 
   if (warp == 0 && lane == 0) {
     cg::prefetch_tmap(&tmA);
     cg::prefetch_tmap(&tmB);
+    // full[s]: one arrival (the leader's expect_tx) + the TMA bytes of every CTA of the pair; tmem_empty: 4 epilogue
+    // warps per CTA of the pair (the peer's warps arrive remotely on the leader's barrier)
     for (int s = 0; s < nst; ++s) { cg::mbar_init(full_bar(s), 1); cg::mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { cg::mbar_init(tfull_bar(a), 1); cg::mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { cg::mbar_init(tfull_bar(a), 1); cg::mbar_init(tempty_bar(a), 4 * CTAS); }
     for (int b = 0; b < 4; ++b) cg::mbar_init(rfull_bar(b), 1);
     cg::fence_barrier_init();
   }
-  if (warp == 1) cg::tmem_alloc(tmem_slot, C::kTmemCols);
+  if (warp == 1) { if (CTAS == 2) cg::tmem_alloc_2cta(tmem_slot, C::kTmemCols); else cg::tmem_alloc(tmem_slot, C::kTmemCols); }
   cg::tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cg::cluster_sync_all();     // the peer's barriers are initialised before anything is signalled on them
   cg::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -442,48 +512,55 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int tiles_m = p.n_img * p.tiles_y * p.tiles_x;
-  const int total_tiles = tiles_m * p.tiles_n;
+  cg::TileSched ts;
+  ts.ctas = CTAS; ts.crank = (int)crank;
+  ts.first = (int)blockIdx.x / CTAS; ts.step = (int)gridDim.x / CTAS;
+  ts.total = ((tiles_m + CTAS - 1) / CTAS) * p.tiles_n;
   const int cin_chunks = p.cin / CG_BK;
   const int nkb = p.ntaps * cin_chunks;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA stages its own A rows and its share of B) =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.tiles_n;
-        const int mt = tile / p.tiles_n;
-        const int xt = mt % p.tiles_x;
-        const int yt = (mt / p.tiles_x) % p.tiles_y;
-        const int img = mt / (p.tiles_x * p.tiles_y);
-        const int x0 = xt * p.tw * p.stride, y0 = yt * p.th * p.stride;
-        const int n0 = nt * BN;
+      for (int w = ts.first; w < ts.total; w += ts.step) {
+        int n0, px0, py0, img;
+        ts.coords(p, BN, w, n0, px0, py0, img);
+        const int x0 = px0 * p.stride, y0 = py0 * p.stride;
+        const int nb0 = n0 + (int)crank * (BN / CTAS);
         for (int t = 0; t < p.ntaps; ++t) {
           const int xi = x0 + p.tap_dx[t], yi = y0 + p.tap_dy[t];
           for (int cc = 0; cc < cin_chunks; ++cc) {
             cg::mbar_wait(empty_bar(stage), phase ^ 1u);
-            cg::mbar_expect_tx(full_bar(stage), (uint32_t)C::kStageBytes);
             const uint32_t a_dst = smem_base + stage * C::kStageBytes;
             const uint32_t b_dst = a_dst + C::kABytes;
-            cg::tma_load_4d(a_dst, &tmA, full_bar(stage), cc * CG_BK, xi, yi, img);
-            cg::tma_load_2d(b_dst, &tmB, full_bar(stage), t * p.cin + cc * CG_BK, n0);
+            if (CTAS == 2) {
+              if (crank == 0) cg::mbar_expect_tx(full_bar(stage), (uint32_t)(2 * C::kStageBytes));
+              const uint32_t lbar = cg::mapa_rank(full_bar(stage), 0);
+              cg::tma_load_4d_2cta(a_dst, &tmA, lbar, cc * CG_BK, xi, yi, img);
+              cg::tma_load_2d_2cta(b_dst, &tmB, lbar, t * p.cin + cc * CG_BK, nb0);
+            } else {
+              cg::mbar_expect_tx(full_bar(stage), (uint32_t)C::kStageBytes);
+              cg::tma_load_4d(a_dst, &tmA, full_bar(stage), cc * CG_BK, xi, yi, img);
+              cg::tma_load_2d(b_dst, &tmB, full_bar(stage), t * p.cin + cc * CG_BK, nb0);
+            }
             if (++stage == nst) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = cg::make_idesc_f16(CG_BM, BN);
+    // ===================== MMA issuer (one thread; of the leader CTA in a pair) =====================
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = cg::make_idesc_f16(CG_BM * CTAS, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        cg::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);     // epilogue has drained this accumulator
+      for (int w = ts.first; w < ts.total; w += ts.step) {
+        cg::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);     // every epilogue warp (of both CTAs) has drained this accumulator
         cg::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < nkb; ++kb) {
-          cg::mbar_wait(full_bar(stage), phase);              // TMA bytes have landed
+          cg::mbar_wait(full_bar(stage), phase);              // TMA bytes (of both CTAs) have landed
           cg::tc_fence_after();
           const uint32_t a_addr = smem_base + stage * C::kStageBytes;
           const uint64_t adesc = cg::make_sw128_desc(a_addr);
@@ -491,12 +568,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           #pragma unroll
           for (int k = 0; k < CG_BK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128-B swizzle atom: +2 in 16-B units
-            cg::umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            if (CTAS == 2) cg::umma_f16_2cta(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            else cg::umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
           }
-          cg::umma_commit(empty_bar(stage));                   // frees the smem slot when the MMAs retire
+          // frees the smem slot (in both CTAs) when the MMAs retire
+          if (CTAS == 2) cg::umma_commit_2cta(empty_bar(stage)); else cg::umma_commit(empty_bar(stage));
           if (++stage == nst) { stage = 0; phase ^= 1u; }
         }
-        cg::umma_commit(tfull_bar(acc));                       // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (CTAS == 2) cg::umma_commit_2cta(tfull_bar(acc)); else cg::umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -507,29 +587,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0; uint32_t acc_phase = 0;
     if (p.maskdot) {
       float* bias_gen = reinterpret_cast<float*>(smem_gen + ring_bytes);       // bias + class weights live in the (unused) staging area
-      cg::epilogue_maskdot<BN>(p, bias_gen, tfull_bar(0), tempty_bar(0), tmem_base, total_tiles, warp, lane);
+      cg::epilogue_maskdot<BN>(p, bias_gen, tfull_bar(0), tempty_bar(0), tmem_base, ts, warp, lane);
     } else if (p.tma_out) {
       const uint32_t rf0 = rfull_bar(0), tf0 = tfull_bar(0), te0 = tempty_bar(0);
       uint8_t* out_gen = smem_gen + ring_bytes;
       float* bias_gen = reinterpret_cast<float*>(out_gen + out_bytes + 256);
-      if (p.tma_res) cg::epilogue_staged<BN, 1>(p, &tmC, &tmR, out_gen, out_base, bias_gen, rf0, tf0, te0, tmem_base, total_tiles, warp, lane);
-      else if (p.res_mode == 2) cg::epilogue_staged<BN, 2>(p, &tmC, &tmR, out_gen, out_base, bias_gen, rf0, tf0, te0, tmem_base, total_tiles, warp, lane);
-      else cg::epilogue_staged<BN, 0>(p, &tmC, &tmR, out_gen, out_base, bias_gen, rf0, tf0, te0, tmem_base, total_tiles, warp, lane);
+      if (p.tma_res) cg::epilogue_staged<BN, 1>(p, &tmC, &tmR, out_gen, out_base, bias_gen, rf0, tf0, te0, tmem_base, ts, warp, lane);
+      else if (p.res_mode == 2) cg::epilogue_staged<BN, 2>(p, &tmC, &tmR, out_gen, out_base, bias_gen, rf0, tf0, te0, tmem_base, ts, warp, lane);
+      else cg::epilogue_staged<BN, 0>(p, &tmC, &tmR, out_gen, out_base, bias_gen, rf0, tf0, te0, tmem_base, ts, warp, lane);
     } else
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.tiles_n;
-      const int mt = tile / p.tiles_n;
-      const int xt = mt % p.tiles_x;
-      const int yt = (mt / p.tiles_x) % p.tiles_y;
-      const int img = mt / (p.tiles_x * p.tiles_y);
-      const int x = xt * p.tw + (row % p.tw);
-      const int y = yt * p.th + (row / p.tw);
-      const bool pix_ok = (x < p.w_out) && (y < p.h_out);
-      const int n0 = nt * BN;
+    for (int tile = ts.first; tile < ts.total; tile += ts.step) {
+      int n0, tx0, ty0, img;
+      ts.coords(p, BN, tile, n0, tx0, ty0, img);
+      const int x = tx0 + (row % p.tw);
+      const int y = ty0 + (row / p.tw);
+      const bool pix_ok = (x < p.w_out) && (y < p.h_out) && (img < p.n_img);
       cg::mbar_wait(tfull_bar(acc), acc_phase);
       cg::tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-
       // output / residual row pointers
       size_t out_off;
       int ch_base = n0;
@@ -593,15 +668,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       cg::tc_fence_before();
       __syncwarp();
-      if (lane == 0) cg::mbar_arrive(tempty_bar(acc));
+      if (lane == 0) cg::tempty_arrive(ts, tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
-  // teardown
+  // teardown: nobody leaves (or frees TMEM) while the partner may still read this CTA's smem / signal its barriers
   cg::tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cg::cluster_sync_all();
   if (warp == 1) {
     cg::tc_fence_after();
-    cg::tmem_dealloc(tmem_base, C::kTmemCols);
+    if (CTAS == 2) cg::tmem_dealloc_2cta(tmem_base, C::kTmemCols); else cg::tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }

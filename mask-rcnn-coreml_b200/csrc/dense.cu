@@ -21,33 +21,43 @@ static PFN_tmapEncodeTiled get_encode_fn() {
   return fn;
 }
 
-template <int BN>
+template <int BN, int CTAS>
 static int launch_bn(mrcnn_ctx* ctx, const ConvPlan& plan) {
   static bool attr_done = false;
   if (!attr_done) {
-    MRCNN_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             cg::Cfg<BN>::kSmemBytes));
+    MRCNN_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_gemm_kernel<BN, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             cg::Cfg<BN, CTAS>::kSmemBytes));
     attr_done = true;
   }
   ProfScope ps(ctx, PROF_CONV_GEMM, plan.flops);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(plan.grid); cfg.blockDim = dim3(CG_THREADS);
-  cfg.dynamicSmemBytes = cg::Cfg<BN>::kSmemBytes; cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
+  cfg.dynamicSmemBytes = cg::Cfg<BN, CTAS>::kSmemBytes; cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // PDL: see griddepcontrol.wait in the kernel
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  MRCNN_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN>, plan.tmA, plan.tmB, plan.tmC, plan.tmR, plan.p));
+  attr[1].id = cudaLaunchAttributeClusterDimension;                    // CTA pairs for tcgen05.mma.cta_group::2
+  attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = CTAS == 2 ? 2 : 1;
+  MRCNN_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, CTAS>, plan.tmA, plan.tmB, plan.tmC, plan.tmR, plan.p));
   MRCNN_LAUNCH_CHECK(ctx);
   return MRCNN_OK;
 }
 
 int conv_plan_run(mrcnn_ctx* ctx, const ConvPlan& plan) {
+  if (plan.p.ctas == 2) {
+    switch (plan.bn) {
+      case 64: return launch_bn<64, 2>(ctx, plan);
+      case 128: return launch_bn<128, 2>(ctx, plan);
+      case 256: return launch_bn<256, 2>(ctx, plan);
+    }
+    return mrcnn_fail(ctx, MRCNN_EINVAL, "conv: unsupported BN for CTA pairs");
+  }
   switch (plan.bn) {
-    case 32: return launch_bn<32>(ctx, plan);
-    case 64: return launch_bn<64>(ctx, plan);
-    case 128: return launch_bn<128>(ctx, plan);
-    case 256: return launch_bn<256>(ctx, plan);
+    case 32: return launch_bn<32, 1>(ctx, plan);
+    case 64: return launch_bn<64, 1>(ctx, plan);
+    case 128: return launch_bn<128, 1>(ctx, plan);
+    case 256: return launch_bn<256, 1>(ctx, plan);
   }
   return mrcnn_fail(ctx, MRCNN_EINVAL, "conv: unsupported BN");
 }
@@ -103,8 +113,23 @@ int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan) {
       }
   }
   plan->bn = bn;
-  const long total_tiles = (long)p.n_img * p.tiles_x * p.tiles_y * p.tiles_n;
-  plan->grid = (int)(total_tiles < ctx->sm_count ? total_tiles : ctx->sm_count);
+  // CTA pairs (cta_group::2): two adjacent M tiles share one 256-row MMA; used when there is enough work for pairs
+  const long tiles_m = (long)p.n_img * p.tiles_x * p.tiles_y;
+  int ctas = L.ctas;
+  if (!ctas) {
+    static int env_ctas = -1;
+    if (env_ctas < 0) { const char* e = getenv("MRCNN_CONV_CTAS"); env_ctas = e ? atoi(e) : 0; }
+    // measured on B200 (profiles/r1j_conv_layers_ctas{1,2}.txt): pairs win on compute-bound layers (>= 8 K blocks per
+    // tile: 3x3 convs, the head GEMMs), single CTAs on the memory-bound 1x1 layers and on layers with a TMA residual
+    const int nkb_all = ntaps * (L.cin / CG_BK);
+    const bool compute_bound = nkb_all >= 8 && !(L.residual && L.res_mode == 1);
+    ctas = env_ctas ? env_ctas : ((bn >= 64 && tiles_m >= 2 && compute_bound) ? 2 : 1);
+  }
+  if (bn < 64 || tiles_m < 2) ctas = 1;
+  p.ctas = ctas;
+  const long total_items = ((tiles_m + ctas - 1) / ctas) * p.tiles_n;
+  const long slots = ctx->sm_count / ctas;
+  plan->grid = (int)((total_items < slots ? total_items : slots) * ctas);
   plan->flops = 2.0 * p.n_img * p.h_out * p.w_out * (double)L.cout * ntaps * L.cin;
 
   // ---- A: 4-D (C, W, H, N) view of the NHWC activation, box (64, tw*s, th*s, 1), traversal stride s
@@ -130,7 +155,7 @@ int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan) {
   // ---- B: 2-D (K, Cout) K-major weights, box (64, BN)
   cuuint64_t bdims[2] = {(cuuint64_t)ntaps * L.cin, (cuuint64_t)L.cout};
   cuuint64_t bstr[1] = {(cuuint64_t)ntaps * L.cin * 2};
-  cuuint32_t bbox[2] = {(cuuint32_t)CG_BK, (cuuint32_t)bn};
+  cuuint32_t bbox[2] = {(cuuint32_t)CG_BK, (cuuint32_t)(bn / ctas)};      // a CTA of a pair stages half of the B tile
   cuuint32_t bes[2] = {1, 1};
   r = enc(&plan->tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)L.w, bdims, bstr, bbox, bes,
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -155,9 +180,9 @@ int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan) {
   {
     const int nkb = ntaps * (L.cin / CG_BK);
     const bool deep_staging = p.tma_out && (p.tma_res || nkb <= 4);
-    const int deep[4] = {8, 8, 6, 4}, shrt[4] = {6, 6, 5, 3};     // BN = 32, 64, 128, 256
+    const int deep[2][4] = {{8, 8, 6, 4}, {8, 8, 8, 6}}, shrt[2][4] = {{6, 6, 5, 3}, {8, 8, 6, 5}};     // [ctas-1][BN = 32, 64, 128, 256]
     const int bi = bn == 32 ? 0 : (bn == 64 ? 1 : (bn == 128 ? 2 : 3));
-    p.nstages = deep_staging ? shrt[bi] : deep[bi];
+    p.nstages = deep_staging ? shrt[ctas - 1][bi] : deep[ctas - 1][bi];
     p.nbuf_log2 = deep_staging ? 2 : 1;
   }
   if (p.tma_out) {
