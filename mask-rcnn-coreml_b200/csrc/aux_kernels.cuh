@@ -151,21 +151,43 @@ __global__ void cls_post_kernel(const float* __restrict__ logits, int64_t total,
 
 // Slot bookkeeping of TimeDistributedMaskLayer (:52, :58-60, :71, :87-89):
 //   valid blocks are compacted (index j), block a gets class detections[j*6+4] (Q14),
-//   then rows [count(valid), D) are zeroed.  One thread per image (D is small).
-__global__ void mask_slots_kernel(const int32_t* __restrict__ block_valid, const float* __restrict__ det, int D,
-                                  int32_t* __restrict__ slot_valid, int32_t* __restrict__ slot_cls) {
-  const int img = blockIdx.x;
-  if (threadIdx.x != 0) return;
+//   then rows [count(valid), D) are zeroed.  One CTA per image, ballot-based ordered compaction.
+__global__ void __launch_bounds__(256)
+mask_slots_kernel(const int32_t* __restrict__ block_valid, const float* __restrict__ det, int D,
+                  int32_t* __restrict__ slot_valid, int32_t* __restrict__ slot_cls) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base, s_total;
+  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int32_t* v = block_valid + (int64_t)img * D;
   const float* dd = det + (int64_t)img * D * 6;
-  int cnt = 0;
-  for (int a = 0; a < D; ++a) cnt += v[a] ? 1 : 0;
-  int j = 0;
-  for (int a = 0; a < D; ++a) {
-    int ok = v[a] && (a < cnt);
-    slot_cls[(int64_t)img * D + a] = v[a] ? (int)dd[j * 6 + 4] : 0;
-    slot_valid[(int64_t)img * D + a] = ok;
-    if (v[a]) ++j;
+  // pass 1: number of valid blocks
+  int c = 0;
+  for (int a = tid; a < D; a += 256) c += v[a] ? 1 : 0;
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) s_warp[wid] = c;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  if (tid == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_warp[w]; s_total = t; }
+  __syncthreads();
+  const int cnt = s_total;
+  // pass 2: ordered compaction index j of every valid block (chunks of 256 slots)
+  for (int start = 0; start < D; start += 256) {
+    const int a = start + tid;
+    const bool ok = a < D && v[a];
+    const unsigned int bal = __ballot_sync(0xffffffffu, ok);
+    __syncthreads();
+    if (lane == 0) s_warp[wid] = __popc(bal);
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < wid; ++w) before += s_warp[w];
+    const int j = before + __popc(bal & ((1u << lane) - 1u));
+    if (a < D) {
+      slot_cls[(int64_t)img * D + a] = ok ? (int)dd[j * 6 + 4] : 0;       // class of the j-th detection (Q14)
+      slot_valid[(int64_t)img * D + a] = (ok && a < cnt) ? 1 : 0;          // rows [count(valid), D) are zeroed (:87-89)
+    }
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_warp[w]; s_base += t; }
   }
 }
 

@@ -473,7 +473,7 @@ static int mask_tail(mrcnn_ctx* ctx, int batch, int D, const float* d_det, float
   int32_t* slot_cls = (int32_t*)m->bufs["mask_slot_cls"].p;
   {
     ProfScope ps(ctx, PROF_GLUE, (double)M * 40.0);
-    mask_slots_kernel<<<batch, 32, 0, ctx->stream>>>(valid, d_det, D, slot_valid, slot_cls);
+    mask_slots_kernel<<<batch, 256, 0, ctx->stream>>>(valid, d_det, D, slot_valid, slot_cls);
     MRCNN_LAUNCH_CHECK(ctx);
   }
   it->second->p.out = d_out;
