@@ -256,7 +256,8 @@ MRCNN_API int mrcnn_predict_allgather(mrcnn_ctx* ctx, int batch_local, const uin
 MRCNN_API int mrcnn_last_stage_times(const mrcnn_ctx* ctx, int max_stages,
                            const char** names_out, float* ms_out);
 /* Per-kernel-class device timing: while enabled, every kernel launch of this
- * library is bracketed by a CUDA event pair on the context's stream.
+ * library is bracketed by a CUDA event pair on the context's stream (consecutive launches of the same class
+ * share one pair, so back-to-back kernels are timed as they run in production).
  * mrcnn_profile_read synchronises, then returns per class (static name) the summed
  * milliseconds, the number of bracketed launches and their algorithmic work
  * (bytes for the memory-bound classes, flops for conv_gemm_tcgen05) since the last

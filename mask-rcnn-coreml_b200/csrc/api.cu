@@ -215,7 +215,7 @@ int mrcnn_profile_read(mrcnn_ctx* ctx, int max_classes, const char** names_out, 
   double work[PROF_NUM_CLASSES] = {0};
   for (auto& r : ctx->prof_recs) {
     float t = 0.f;
-    if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { ms[r.cls] += t; cnt[r.cls]++; work[r.cls] += r.work; }
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { ms[r.cls] += t; cnt[r.cls] += r.launches; work[r.cls] += r.work; }
   }
   ctx->prof_recs.clear();
   ctx->prof_used = 0;

@@ -71,7 +71,7 @@ struct mrcnn_ctx {
 
   // ---- per-kernel-class device timing (mrcnn_profile_*) ----
   bool profiling = false;
-  struct ProfRec { int cls; cudaEvent_t e0, e1; double work; };
+  struct ProfRec { int cls; cudaEvent_t e0, e1; double work; int launches; };
   std::vector<ProfRec> prof_recs;      // recorded since the last read
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pool;  // reusable event pairs
   size_t prof_used = 0;
@@ -90,6 +90,14 @@ struct ProfScope {
   mrcnn_ctx* ctx; int idx = -1;
   ProfScope(mrcnn_ctx* c, int cls, double work) : ctx(c) {
     if (!c->profiling) return;
+    // consecutive scopes of the same class share one event pair (only the end event is re-recorded), so that
+    // back-to-back launches of a class are timed as they run in production: no event between them
+    if (!c->prof_recs.empty() && c->prof_recs.back().cls == cls) {
+      idx = (int)c->prof_recs.size() - 1;
+      c->prof_recs[idx].work += work;
+      c->prof_recs[idx].launches += 1;
+      return;
+    }
     if (c->prof_used == c->prof_pool.size()) {
       cudaEvent_t a, b;
       if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
@@ -97,7 +105,7 @@ struct ProfScope {
     }
     auto& pr = c->prof_pool[c->prof_used++];
     cudaEventRecord(pr.first, c->stream);
-    c->prof_recs.push_back({cls, pr.first, pr.second, work});
+    c->prof_recs.push_back({cls, pr.first, pr.second, work, 1});
     idx = (int)c->prof_recs.size() - 1;
   }
   ~ProfScope() { if (idx >= 0) cudaEventRecord(ctx->prof_recs[idx].e1, ctx->stream); }

@@ -123,7 +123,7 @@ int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan) {
     // tile: 3x3 convs, the head GEMMs), single CTAs on the memory-bound 1x1 layers and on layers with a TMA residual
     const int nkb_all = ntaps * (L.cin / CG_BK);
     const bool compute_bound = nkb_all >= 8 && !(L.residual && L.res_mode == 1);
-    ctas = env_ctas ? env_ctas : ((bn >= 64 && tiles_m >= 2 && compute_bound) ? 2 : 1);
+    ctas = env_ctas ? env_ctas : ((bn == 256 && tiles_m >= 2 && compute_bound) ? 2 : 1);
   }
   if (bn < 64 || tiles_m < 2) ctas = 1;
   p.ctas = ctas;

@@ -153,7 +153,32 @@ det_finalize_percls_kernel(const float4* __restrict__ fbox, const float* __restr
     if (box_selectable(b[i])) atomicOr(&valid[i >> 6], bit);
   }
   __syncthreads();
-  if (tid < ncls_cap) {
+  if (tid < ncls_cap && nwords <= 16) {
+    // removal words of this class live in registers (R <= 1024): the row ORs of a kept box are independent loads
+    const unsigned long long* cb = cbits + (size_t)tid * words;
+    unsigned long long rm[16];
+    #pragma unroll
+    for (int ww = 0; ww < 16; ++ww) rm[ww] = 0ull;
+    int count = 0;
+    #pragma unroll
+    for (int w = 0; w < 16; ++w) {
+      if (w < nwords && count < max_det) {
+        unsigned long long alive = cb[w] & valid[w] & ~rm[w];
+        while (alive && count < max_det) {
+          const int t = __ffsll((long long)alive) - 1;
+          const unsigned long long bit = 1ull << t;
+          alive &= ~bit;
+          const int i = (w << 6) + t;
+          atomicOr(&keptbits[w], bit);
+          ++count;
+          const unsigned long long* row = smask + (size_t)i * nwords;
+          alive &= ~row[w];
+          #pragma unroll
+          for (int ww = 0; ww < 16; ++ww) if (ww > w && ww < nwords) rm[ww] |= row[ww];
+        }
+      }
+    }
+  } else if (tid < ncls_cap) {
     const unsigned long long* cb = cbits + (size_t)tid * words;
     unsigned long long* rm = rem + (size_t)tid * words;
     int count = 0;

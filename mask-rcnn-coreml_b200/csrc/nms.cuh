@@ -30,11 +30,15 @@ nms_mask_kernel(const float4* __restrict__ boxes, const float* __restrict__ cls,
   __shared__ RectD col_rect[NMS_TILE];
   __shared__ float4 col_f[NMS_TILE];      // (x1, y1, ub(maxx), ub(maxy)) in fp32, upper bounds rounded up
   __shared__ float col_cls[NMS_TILE];
+  __shared__ float4 col_box[NMS_TILE];    // (y1, x1, y2, x2) as given
+  __shared__ float col_area[NMS_TILE];    // fp32 area estimate (sign-exact: zero / negative exactly when the fp64 area is)
   const int t = threadIdx.x;
   const int cj = cb * NMS_TILE + t;
   if (cj < n) {
     const RectD rc = make_rect(b[cj]);
     col_rect[t] = rc;
+    col_box[t] = b[cj];
+    col_area[t] = (b[cj].w - b[cj].y) * (b[cj].z - b[cj].x);
     col_f[t] = make_float4(b[cj].y, b[cj].x, __double2float_ru(rc.maxx), __double2float_ru(rc.maxy));
     col_cls[t] = c ? c[cj] : 0.0f;
   }
@@ -45,6 +49,8 @@ nms_mask_kernel(const float4* __restrict__ boxes, const float* __restrict__ cls,
   const float mx1 = b[i].y, my1 = b[i].x;
   const float mubx = __double2float_ru(me.maxx), muby = __double2float_ru(me.maxy);
   const float mycls = c ? c[i] : 0.0f;
+  const float4 mb = b[i];
+  const float marea = (mb.w - mb.y) * (mb.z - mb.x);
   const int ncol = min(NMS_TILE, n - cb * NMS_TILE);
   const bool prefilter = thr >= 0.0f;     // IoU of a disjoint pair is exactly 0, never > a non-negative threshold
   unsigned long long bits = 0ull;
@@ -55,7 +61,17 @@ nms_mask_kernel(const float4* __restrict__ boxes, const float* __restrict__ cls,
     // do not overlap (intersection width or height <= 0 -> IoU 0 in the exact fp64 formula as well)
     const float4 cf = col_f[j];
     if (prefilter && ((cf.z <= mx1) || (mubx <= cf.x) || (cf.w <= my1) || (muby <= cf.y))) continue;
-    if (iou_rect(col_rect[j], me) > thr) bits |= (1ull << j);
+    // overlapping pair: decide in fp32 when the fp32 IoU is further than 1e-4 from the threshold (its error against
+    // the exact formula is below 1e-6: a handful of roundings, and union >= max(area) so nothing cancels); only
+    // borderline pairs take the exact path (fp64 IoU rounded to fp32, Utils.swift:232-246)
+    const float4 cb4 = col_box[j];
+    const float iw = fminf(mb.w, cb4.w) - fmaxf(mb.y, cb4.y), ih = fminf(mb.z, cb4.z) - fmaxf(mb.x, cb4.x);
+    const float inter = fmaxf(iw, 0.0f) * fmaxf(ih, 0.0f);
+    const float i32 = inter / (marea + col_area[j] - inter);
+    bool sup;
+    if (prefilter && marea > 0.0f && col_area[j] > 0.0f && fabsf(i32 - thr) > 1e-4f) sup = i32 > thr;
+    else sup = iou_rect(col_rect[j], me) > thr;
+    if (sup) bits |= (1ull << j);
   }
   mask[((size_t)img * stride_boxes + i) * words + cb] = bits;
 }
