@@ -286,6 +286,9 @@ MRCNN_API int mrcnn_conv2d_nhwc_f16(mrcnn_ctx* ctx, const void* x, int n, int h,
                           int cin, const void* wgt, const float* bias, int cout,
                           int kh, int kw, int stride, int pad,
                           const void* residual, int relu, void* out);
+/* Debug: per-CTA event trace (clock64 stamps of the producer / MMA / epilogue roles) of the next
+ * mrcnn_conv2d_nhwc_f16 calls; device buffer of 148 * 3 * (2*340 + 2) u64, NULL = off (tools/trace_conv.py). */
+MRCNN_API int mrcnn_debug_conv_trace(void* device_buffer);
 /* Backbone + FPN + RPN only (stage-level parity hook; device pointers only):
  *   rgb [batch,H,W,3] u8 -> fmaps_out[l] [batch,H_l,W_l,256] f16 NHWC (P2..P5),
  *   probs_out [batch,N,2] f32, deltas_out [batch,N,4] f32. */

@@ -77,6 +77,7 @@ SIGNATURES = {
     "mrcnn_profile_read": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(_i64), C.POINTER(C.c_double)]),
     "mrcnn_roialign_nhwc_f16": (_i, [_vp, _i, _vp, _i, _i64, C.POINTER(_vp), C.POINTER(C.c_int32), _i64, _i, _vp, _vp]),
     "mrcnn_conv2d_nhwc_f16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "mrcnn_debug_conv_trace": (_i, [_vp]),
     "mrcnn_backbone_eval": (_i, [_vp, _i, _vp, C.POINTER(_vp), _vp, _vp]),
 }
 

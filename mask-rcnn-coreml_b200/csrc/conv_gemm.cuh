@@ -56,6 +56,7 @@ struct ConvGemmParams {
   int deconv_c;
   int tma_out;                 // 1: fp16 NHWC output staged in smem and written with TMA stores (cout % 64 == 0)
   int tma_res;                 // 1: residual (res_mode 1) tiles fetched with TMA into the same staging buffers
+  unsigned long long* trace;   // debug: per-CTA event trace (clock64 stamps), nullptr in production (tools/trace_conv.py)
   int ctas;                    // 1 or 2 (CTA pair / cta_group::2), must match the kernel instantiation and the cluster launch
   int nstages;                 // depth of the operand ring (A+B tiles), chosen per layer by the host
   int nbuf_log2;               // log2 of the number of 16 KB output / residual staging buffers (1 or 2)
@@ -176,6 +177,24 @@ __device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, u
 __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+// debug event trace: per CTA three role sections (0 producer, 1 MMA, 2 epilogue) of CG_TRACE_MAX (code << 32 | arg,
+// clock64) pairs, slot 0 of a section = its event count.  Plain stores with a per-thread cursor: nothing on the
+// critical path waits for them.
+#define CG_TRACE_MAX 340
+struct TraceCursor { unsigned long long* base; uint32_t n; };
+__device__ __forceinline__ TraceCursor trace_open(const ConvGemmParams& p, int role) {
+  TraceCursor c; c.n = 0;
+  c.base = p.trace ? p.trace + ((size_t)blockIdx.x * 3 + role) * (2 * CG_TRACE_MAX + 2) : nullptr;
+  return c;
+}
+__device__ __forceinline__ void trace_ev(TraceCursor& c, uint32_t code, uint32_t arg) {
+  if (c.base && c.n < CG_TRACE_MAX) {
+    c.base[2 + 2 * c.n] = ((unsigned long long)code << 32) | arg;
+    c.base[3 + 2 * c.n] = (unsigned long long)clock64();
+    c.base[0] = ++c.n;
+  }
 }
 
 // The work items of one CTA: item w = first, first + step, ... < total.  An item is a 128 x BN tile (CTAS = 1) or the
@@ -302,6 +321,8 @@ __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, const C
     mbar_expect_tx(rfull0 + 8u * b, (uint32_t)kStageBytes);
     tma_load_4d(out_base + b * (uint32_t)kStageBytes, tmR, rfull0 + 8u * b, n0 + (int)(j % (uint32_t)nchunks) * 64, x0, y0, img);
   };
+  TraceCursor tc = trace_open(p, 2);
+  if (!e0) tc.base = nullptr;
   if (e0) { prefetch_tmap(tmC); if (RES == 1) prefetch_tmap(tmR); }
   if (RES == 1 && e0) for (uint32_t j = 0; j < nb_mask; ++j) load_residual(j);     // prefetch distance = nbuf - 1 chunks
   const uint32_t row_off = (uint32_t)row * 128u;
@@ -324,6 +345,7 @@ __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, const C
       epi_bar_sync();
     }
     mbar_wait(tfull0 + 8u * acc, acc_phase);
+    trace_ev(tc, 5, (uint32_t)tile);                  // epilogue: accumulator ready
     tc_fence_after();
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
     #pragma unroll 1
@@ -378,6 +400,7 @@ __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, const C
         const uint32_t sbuf = out_base + buf * (uint32_t)kStageBytes;
         tma_store_4d(tmC, sbuf, nc, x0, y0, img);
         bulk_commit();
+        trace_ev(tc, 6, (uint32_t)c);                          // epilogue: chunk stored
         if (RES == 1) {
           bulk_wait_read<1>();             // store cc-1 has finished reading its buffer ...
           load_residual(cc + nb_mask);     // ... which is the buffer of chunk cc + nbuf - 1: fetch that chunk's residual
@@ -523,6 +546,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== TMA producer (every CTA stages its own A rows and its share of B) =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      cg::TraceCursor tc = cg::trace_open(p, 0);
       for (int w = ts.first; w < ts.total; w += ts.step) {
         int n0, px0, py0, img;
         ts.coords(p, BN, w, n0, px0, py0, img);
@@ -532,6 +556,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int xi = x0 + p.tap_dx[t], yi = y0 + p.tap_dy[t];
           for (int cc = 0; cc < cin_chunks; ++cc) {
             cg::mbar_wait(empty_bar(stage), phase ^ 1u);
+            cg::trace_ev(tc, 1, (uint32_t)stage);             // producer: slot free, issuing loads
             const uint32_t a_dst = smem_base + stage * C::kStageBytes;
             const uint32_t b_dst = a_dst + C::kABytes;
             if (CTAS == 2) {
@@ -555,12 +580,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t idesc = cg::make_idesc_f16(CG_BM * CTAS, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      cg::TraceCursor tc = cg::trace_open(p, 1);
       for (int w = ts.first; w < ts.total; w += ts.step) {
         cg::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);     // every epilogue warp (of both CTAs) has drained this accumulator
+        cg::trace_ev(tc, 3, (uint32_t)w);                     // MMA: accumulator free, tile start
         cg::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < nkb; ++kb) {
           cg::mbar_wait(full_bar(stage), phase);              // TMA bytes (of both CTAs) have landed
+          cg::trace_ev(tc, 2, (uint32_t)kb);                   // MMA: operands landed
           cg::tc_fence_after();
           const uint32_t a_addr = smem_base + stage * C::kStageBytes;
           const uint64_t adesc = cg::make_sw128_desc(a_addr);
@@ -577,6 +605,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         // accumulator complete -> epilogue warps (of both CTAs)
         if (CTAS == 2) cg::umma_commit_2cta(tfull_bar(acc)); else cg::umma_commit(tfull_bar(acc));
+        cg::trace_ev(tc, 4, (uint32_t)w);                     // MMA: all MMAs of the tile issued
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }

@@ -169,6 +169,7 @@ int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan) {
   plan->tmC = plan->tmB; plan->tmR = plan->tmB;      // valid placeholders when the staged epilogue is off
   p.tma_out = (!L.no_tma_epilogue && !L.out_f32 && !L.deconv && (L.cout % 64) == 0 && bn >= 64) ? 1 : 0;
   p.tma_res = (p.tma_out && p.res_mode == 1) ? 1 : 0;
+  p.trace = L.trace;
   p.maskdot = L.maskdot;
   if (L.maskdot) {
     MRCNN_REQUIRE(ctx, L.deconv && L.deconv_c == 256 && bn == 256 && L.bias && L.md_valid && L.md_cls && L.md_w && L.md_b && L.md_ncls > 0,
@@ -204,7 +205,13 @@ int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan) {
   return MRCNN_OK;
 }
 
+static unsigned long long* g_trace_buf = nullptr;   // set by mrcnn_debug_conv_trace; picked up by the conv2d hook only
+
 extern "C" {
+
+// Debug: device buffer of gridDim * 3 * (2 * 340 + 2) u64 that the NEXT mrcnn_conv2d_nhwc_f16 calls write their per-CTA event
+// traces into (tools/trace_conv.py); NULL switches tracing off.  Not part of the reference-facing surface.
+MRCNN_API int mrcnn_debug_conv_trace(void* device_buffer) { g_trace_buf = (unsigned long long*)device_buffer; return MRCNN_OK; }
 
 // Test / bench hook: one NHWC fp16 convolution through the tcgen05 kernel.
 //   x [n,h,w,cin] f16, wgt [cout,kh,kw,cin] f16, bias [cout] f32 or NULL,
@@ -220,6 +227,7 @@ MRCNN_API int mrcnn_conv2d_nhwc_f16(mrcnn_ctx* ctx, const void* x, int n, int h,
   L.w = (const __half*)wgt; L.cout = cout; L.kh = kh; L.kw = kw; L.stride = stride; L.pad = pad;
   L.bias = bias; L.residual = (const __half*)residual; L.res_mode = residual ? 1 : 0;
   L.relu = relu; L.out = out;
+  L.trace = g_trace_buf;
   ConvPlan plan;
   int rc = conv_plan_build(ctx, L, &plan);
   if (rc) return rc;

@@ -27,6 +27,7 @@ struct ConvLaunch {
   int h_out = 0, w_out = 0;      // 0 -> derived from kh/kw/stride/pad
   int ldc = 0;                   // 0 -> round_up(cout, 8)
   int tw = 0, th = 0, bn = 0;    // 0 -> auto
+  unsigned long long* trace = nullptr;   // debug event trace buffer (device), see cg::trace_ev
   int ctas = 0;                  // 0 -> auto (env MRCNN_CONV_CTAS overrides), 1 = one CTA per tile, 2 = CTA pairs (cta_group::2)
   int no_tma_epilogue = 0;       // force the direct-store epilogue (tests)
   // mask-head tail fused into the deconv epilogue (needs deconv = 1, deconv_c == bn == 256): out = f32 [n, 2h, 2w]
