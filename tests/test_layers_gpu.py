@@ -240,3 +240,48 @@ def test_letterbox_matches_oracle(pkg, orc):
         pkg._cabi.check(c.handle, pkg.lib().mrcnn_letterbox_eval(c.handle, pkg._cabi.ptr(img), h, w, pkg._cabi.ptr(out)))
         np.testing.assert_array_equal(out, orc.letterbox(img, 256, 256))           # bit-exact (same fp64 op order)
     c.close()
+
+
+@pytest.mark.parametrize("seed,n,pre,mx,thr", [(1, 3000, 700, 120, 0.7), (2, 10000, 1500, 300, 0.5), (3, 777, 777, 64, 0.9),
+                                               (4, 50000, 6000, 1000, 0.7), (5, 4097, 2048, 2048, 0.3), (6, 129, 65, 65, 0.6)])
+def test_proposal_randomised_configs(pkg, orc, seed, n, pre, mx, thr):
+    """Odd sizes: N not a multiple of the radix tile, pre_nms at / across 64- and 256-box boundaries, max > survivors."""
+    rng = np.random.default_rng(seed)
+    c = pkg.Context(pre_nms_max_proposals=pre, max_proposals=mx, proposal_nms_iou=float(np.float32(thr)))
+    a = pkg.synth.random_rois(n, seed, min_px=10, max_px=400)
+    c.set_anchors(a)
+    p = np.zeros((1, n, 2), np.float32)
+    p[0, :, 1] = np.round(rng.uniform(size=n) * 512) / 512          # many exact ties
+    p[0, :, 0] = 1 - p[0, :, 1]
+    d = (rng.standard_normal((1, n, 4)) * 0.5).astype(np.float32)
+    rois = np.full((1, mx, 4), 3.0, np.float32); keep = np.zeros((1, mx), np.int32); cnt = np.zeros(1, np.int32)
+    pkg.ProposalLayer({"preNMSMaxProposals": pre, "maxProposals": mx, "nmsIOUThreshold": float(np.float32(thr))}, context=c).evaluate(
+        [p, d], [rois], keep, cnt)
+    r0, k0, c0 = orc.proposal(p[0], d[0], a, pre_nms=pre, max_proposals=mx, iou_thr=thr)
+    assert cnt[0] == c0
+    np.testing.assert_array_equal(keep[0], k0)
+    np.testing.assert_array_equal(rois[0], r0)
+    c.close()
+
+
+@pytest.mark.parametrize("seed,r,ncls,maxdet", [(1, 300, 81, 100), (2, 1024, 81, 100), (3, 2000, 81, 100), (4, 1500, 5, 40),
+                                                (5, 65, 300, 10), (6, 4000, 81, 100)])
+def test_detection_randomised_configs(pkg, orc, seed, r, ncls, maxdet):
+    """Exercises the register path (<= 1024 rois), the shared-memory path and the generic sequential fallback
+    (bitmaps larger than shared memory) of the per-class NMS, few / many classes and small per-class caps."""
+    rng = np.random.default_rng(100 + seed)
+    c = pkg.Context(num_classes=ncls, max_detections=maxdet)
+    rois = pkg.synth.random_rois(r, seed, min_px=20, max_px=300)
+    centres = rng.integers(0, 12, r)
+    rois = np.clip(rois * 0.2 + (centres[:, None] / 16.0 + 0.05), 0, 1).astype(np.float32)       # 12 heavy clusters
+    cls = np.zeros((1, r, 6), np.float32)
+    cls[0, :, :4] = (rng.standard_normal((r, 4)) * 0.3).astype(np.float32)
+    cls[0, :, 4] = rng.integers(0, min(ncls, 9), r)                  # class 0 = background is filtered
+    cls[0, :, 5] = np.round(rng.uniform(0.5, 1.0, r) * 64) / 64      # ties + below-threshold rows
+    out = np.full((1, maxdet, 6), 9.0, np.float32); keep = np.zeros((1, maxdet), np.int32); cnt = np.zeros(1, np.int32)
+    pkg.DetectionLayer({"maxDetections": maxdet}, context=c).evaluate([rois[None], cls], [out], keep, cnt)
+    o0, k0, c0 = orc.detection(rois, cls[0], max_det=maxdet)
+    assert cnt[0] == c0
+    np.testing.assert_array_equal(keep[0], k0)
+    np.testing.assert_array_equal(out[0], o0)
+    c.close()
