@@ -23,11 +23,12 @@ static PFN_tmapEncodeTiled get_encode_fn() {
 
 template <int BN, int CTAS>
 static int launch_bn(mrcnn_ctx* ctx, const ConvPlan& plan) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {false};      // per device: function attributes belong to the device's context
+  const int dv = ctx->device & 63;
+  if (!attr_done[dv]) {
     MRCNN_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_gemm_kernel<BN, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              cg::Cfg<BN, CTAS>::kSmemBytes));
-    attr_done = true;
+    attr_done[dv] = true;
   }
   ProfScope ps(ctx, PROF_CONV_GEMM, plan.flops);
   cudaLaunchConfig_t cfg = {};

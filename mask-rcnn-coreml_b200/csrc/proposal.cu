@@ -297,12 +297,12 @@ int proposal_run(mrcnn_ctx* ctx, int batch, int64_t N, const float* d_probs, con
   float4 sd = make_float4(cfg.bbox_std[0], cfg.bbox_std[1], cfg.bbox_std[2], cfg.bbox_std[3]);
 #define LAUNCH_SORT(SN)                                                                          \
   do {                                                                                           \
-    static bool attr_set_##SN = false;                                                           \
-    if (!attr_set_##SN) {                                                                        \
+    static bool attr_set_##SN[64] = {false};                                                     \
+    if (!attr_set_##SN[ctx->device & 63]) {                                                      \
       MRCNN_CUDA_TRY(ctx, cudaFuncSetAttribute(sort_decode_kernel<SN>,                           \
                                                cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                                (int)(sizeof(unsigned long long) * SN)));         \
-      attr_set_##SN = true;                                                                      \
+      attr_set_##SN[ctx->device & 63] = true;                                                    \
     }                                                                                            \
     sort_decode_kernel<SN><<<batch, 1024, sizeof(unsigned long long) * SN, s>>>(                                       \
         ctx->d_cand, cand_stride, pre, idx_bits, N, (const float4*)d_deltas,                     \
