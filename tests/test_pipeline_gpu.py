@@ -60,10 +60,10 @@ def test_backbone_fpn_rpn_vs_torch(pkg, small):
     assert probs.shape[1] == small["anchors"].shape[0]
     for l in range(4):
         mx, mean = _relerr(fm[l].astype(np.float32), rfm[l].cpu().numpy())
-        assert mx < 3e-2 and mean < 3e-3, (l, mx, mean)          # fp16 activations: tolerance relative to the map's scale
-    assert np.abs(probs - rprobs.cpu().numpy()).max() < 2e-2
+        assert mx < 6e-3 and mean < 4e-3, (l, mx, mean)          # measured 1.3e-3 / 1.1e-3 (profiles/r1r_dense_errors.txt)
+    assert np.abs(probs - rprobs.cpu().numpy()).max() < 8e-3      # measured 1.5e-3
     mx, mean = _relerr(deltas, rdeltas.cpu().numpy())
-    assert mx < 3e-2 and mean < 3e-3, (mx, mean)
+    assert mx < 6e-3 and mean < 4e-3, (mx, mean)
     assert probs.std() > 0.05                                    # the synthetic RPN is not degenerate
 
 
@@ -79,11 +79,11 @@ def test_classifier_head_vs_torch(pkg, small):
     cls = out[0, :, 4].astype(int)
     # class ids: identical wherever the reference's top-2 margin exceeds the numeric tolerance
     srt = np.sort(probs, axis=1)
-    clear = (srt[:, -1] - srt[:, -2]) > 2e-2
+    clear = (srt[:, -1] - srt[:, -2]) > 5e-3
     assert clear.sum() > 100
     np.testing.assert_array_equal(cls[clear], probs.argmax(1)[clear])
-    np.testing.assert_allclose(out[0, :, 5], probs[np.arange(200), cls], atol=2e-2)
-    np.testing.assert_allclose(out[0, :, :4], bbox[np.arange(200), cls], atol=3e-2 * np.abs(bbox).max())
+    np.testing.assert_allclose(out[0, :, 5], probs[np.arange(200), cls], atol=2e-3)      # measured 2.3e-4
+    np.testing.assert_allclose(out[0, :, :4], bbox[np.arange(200), cls], atol=5e-3 * np.abs(bbox).max())
 
 
 def test_mask_head_vs_torch(pkg, small):
@@ -100,7 +100,7 @@ def test_mask_head_vs_torch(pkg, small):
     pkg.TimeDistributedMaskLayer(context=m.ctx).evaluate([pooled, det], [out])
     ref = Ref(small["folded"], 50).mask(pooled[0, :60].transpose(0, 2, 3, 1)).cpu().numpy()
     want = ref[np.arange(60), det[0, :60, 4].astype(int)]
-    np.testing.assert_allclose(out[0, :60], want, atol=1e-2)
+    np.testing.assert_allclose(out[0, :60], want, atol=2e-3)                               # measured 4.9e-4
     assert not out[0, 60:].any()                                  # TimeDistributedMaskLayer.swift:87-89
     assert 0.05 < out[0, :60].std()
 
