@@ -7,9 +7,11 @@
 //                       ORDERED compaction (roi order is the NMS visiting order,
 //                       Q10), gather, x std, decode, clip (:144-164)
 //   nms_mask_kernel     same-class pairs only (per-class NMS, :170-183)
-//   det_finalize_kernel sequential resolve with a per-class cap of maxDetections,
-//                       then top maxDetections by (score desc, class asc,
-//                       position asc) (:186-209, intended-mode ties), zero pad.
+//   det_finalize_percls_kernel  per-class greedy resolve (one thread per class, bitmask rows staged in
+//                       shared memory) with a per-class cap of maxDetections, then top maxDetections by
+//                       (score desc, class asc, position asc) (:186-209, intended-mode ties), zero pad;
+//                       det_finalize_kernel = the generic sequential resolve, used when the per-class
+//                       bitmaps do not fit in shared memory (> ~1400 rois).
 #include "common.cuh"
 #include "nms.cuh"
 
@@ -255,14 +257,9 @@ int detection_run(mrcnn_ctx* ctx, int batch, int64_t R64, const float* d_rois, c
   MRCNN_REQUIRE(ctx, cfg.num_classes >= 1 && cfg.num_classes <= DET_MAX_CLASSES, "detection: num_classes out of range");
   int rc = detection_ensure_ws(ctx, batch, R64);
   if (rc) return rc;
-  // the workspace stride is the allocated roi capacity; use R itself as stride by
-  // requiring a matching allocation (re-allocate on growth only).
+  // workspace arrays are indexed with stride R (the allocation holds det_rois >= R rois per image)
   const int R = (int)R64;
   const int stride = R;
-  if (ctx->det_rois != R64) {
-    // keep things simple and exact: workspace arrays are indexed with stride R
-    // (they are large enough because det_rois >= R).
-  }
   const int words = ceil_div(R, 64);
   cudaStream_t s = ctx->stream;
   float4 sd = make_float4(cfg.bbox_std[0], cfg.bbox_std[1], cfg.bbox_std[2], cfg.bbox_std[3]);

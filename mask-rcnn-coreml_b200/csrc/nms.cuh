@@ -1,6 +1,8 @@
 // nms.cuh -- greedy NMS (Utils.swift:185-218) as two device stages:
-//   1. nms_mask_kernel: upper-triangular 64x64-tile suppression bitmask, IoU in
-//      fp64 rounded to fp32 and compared with '>' (Utils.swift:203,232-246);
+//   1. nms_mask_kernel: upper-triangular 64x64-tile suppression bitmask.  The reference's test is
+//      Float(IoU in Double) > thr (Utils.swift:203,232-246); pairs whose fp32 IoU is further than 1e-4 from the
+//      threshold are decided in fp32 (two orders of magnitude above its rounding error), borderline pairs with the
+//      exact fp64 formula, so the bitmask equals the reference's decisions bit for bit;
 //   2. nms_resolve(): chunked sequential scan that reproduces the reference's
 //      visiting order exactly (box k is dropped iff an earlier KEPT box overlaps
 //      it), with an optional total cap (ProposalLayer: maxProposals) and an
