@@ -1,0 +1,68 @@
+"""GPU tests at BASELINE.json's full size (ResNet101+FPN, 1024x1024, 6000 -> 1000 proposals, 100 detections) through
+size-independent properties: determinism, batch independence, ordering / padding invariants of the outputs, and
+idempotence of the greedy NMS (its survivors survive again)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def full(pkg):
+    cfg = pkg.MaskRCNNConfig()
+    cfg.maxBatch = 2
+    _, blobs = pkg.weights.synthetic_blobs(101)
+    anchors = pkg.synth.generate_anchors(1024, 1024)
+    model = pkg.MaskRCNN(cfg, blobs=blobs, anchors=anchors)
+    rng = np.random.default_rng(20261)
+    img = rng.integers(0, 256, (2, 128, 128, 3)).astype(np.uint8).repeat(8, 1).repeat(8, 2)
+    img = (img.astype(np.int32) + rng.integers(-25, 25, img.shape)).clip(0, 255).astype(np.uint8)
+    yield {"model": model, "img": img, "anchors": anchors}
+    model.close()
+
+
+def test_fullsize_predict_invariants(pkg, full):
+    m, img = full["model"], full["img"]
+    det, masks = m.prediction_batch(img)
+    det2, masks2 = m.prediction_batch(img)
+    np.testing.assert_array_equal(det, det2)                       # deterministic
+    np.testing.assert_array_equal(masks, masks2)
+    for i in range(2):
+        d1, k1 = m.prediction_batch(img[i:i + 1])
+        np.testing.assert_array_equal(d1[0], det[i])               # images of a batch are independent
+        np.testing.assert_array_equal(k1[0], masks[i])
+        n = int((det[i, :, 5] > 0).sum())
+        assert n > 0
+        s = det[i, :n, 5]
+        assert (np.diff(s) <= 0).all() and (s >= np.float32(0.7)).all()                 # score order, DetectionLayer.swift:199-209
+        assert (det[i, n:] == 0).all() and (masks[i, n:] == 0).all()                    # zero padding :228-231
+        assert ((det[i, :n, 4] >= 1) & (det[i, :n, 4] <= 80) & (det[i, :n, 4] == np.round(det[i, :n, 4]))).all()
+        b = det[i, :n, :4]
+        assert (b >= 0).all() and (b <= 1).all() and (b[:, 2] >= b[:, 0]).all() and (b[:, 3] >= b[:, 1]).all()
+        assert ((masks[i, :n] > 0) & (masks[i, :n] < 1)).all()
+    stages = dict(m.ctx.stage_times())
+    assert stages["Backbone+FPN+RPN"] > 0 and len(stages) == 7
+
+
+def test_fullsize_proposal_nms_idempotent(pkg, full, orc):
+    """The rois kept by ProposalLayer at full size (261,888 anchors -> 6000 -> NMS 0.7) pass its NMS again unchanged,
+    and no kept pair overlaps above the threshold (checked with the oracle's double-precision IoU)."""
+    anchors = full["anchors"]
+    c = pkg.Context()
+    c.set_anchors(anchors)
+    probs, deltas = pkg.synth.rpn_outputs(anchors, 7)
+    rois = np.zeros((1, 1000, 4), np.float32); keep = np.zeros((1, 1000), np.int32); cnt = np.zeros(1, np.int32)
+    pkg.ProposalLayer(context=c).evaluate([probs[None], deltas[None]], [rois], keep, cnt)
+    n = int(cnt[0])
+    assert n == 1000 and len(set(keep[0].tolist())) == 1000 and (probs[keep[0][:-1], 1] >= probs[keep[0][1:], 1]).all()
+    # second pass: the kept boxes as anchors, zero deltas, scores in keep order
+    c2 = pkg.Context(pre_nms_max_proposals=1000, max_proposals=1000)
+    c2.set_anchors(rois[0])
+    p2 = np.zeros((1, 1000, 2), np.float32); p2[0, :, 1] = np.linspace(1.0, 0.5, 1000, dtype=np.float32)
+    r2 = np.zeros((1, 1000, 4), np.float32); k2 = np.zeros((1, 1000), np.int32); c2n = np.zeros(1, np.int32)
+    pkg.ProposalLayer({"preNMSMaxProposals": 1000}, context=c2).evaluate([p2, np.zeros((1, 1000, 4), np.float32)], [r2], k2, c2n)
+    assert c2n[0] == 1000
+    np.testing.assert_array_equal(k2[0], np.arange(1000))
+    idx = np.random.default_rng(0).integers(0, 1000, (400, 2))
+    assert all(orc.iou(rois[0, a], rois[0, b]) <= np.float32(0.7) for a, b in idx if a != b)
+    c.close(); c2.close()
