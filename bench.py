@@ -288,9 +288,10 @@ class PipelineWorkload:
     name = "pipeline"
     dtype = "f16"     # tensor-core operands fp16 (as the reference stores its weights), fp32 accumulate; custom layers f32/f64
 
-    def __init__(self, m, torch, device, batch, rank, world, architecture=101):
+    def __init__(self, m, torch, device, batch, rank, world, architecture=101, precise_masks=False):
         self.m, self.torch, self.b, self.world = m, torch, batch, world
         cfg = m.MaskRCNNConfig()
+        cfg.preciseMasks = bool(precise_masks)
         cfg.architecture = "resnet101" if architecture == 101 else "resnet50"
         cfg.maxBatch = batch
         _, blobs = m.weights.synthetic_blobs(architecture)
@@ -310,7 +311,9 @@ class PipelineWorkload:
         self.h2d = self.h_img.numel()
         self.d2h = 4 * (self.h_det.numel() + self.h_mask.numel())
         self.config_extra = {"model": "ResNet101+FPN Mask-RCNN, 81 classes, synthetic fp16 weights (seed 7)",
-                             "collective": "none" if world == 1 else "1 ncclAllGather of packed detections|masks per step"}
+                             "collective": "none" if world == 1 else "1 ncclAllGather of packed detections|masks per step",
+                             "mask_head": "2-term fp16 activations (masks within 1e-4 of fp32)" if precise_masks else
+                                          "fp16 activations (masks within 5e-4 of fp32)"}
         if world > 1:
             import torch.distributed as dist
             uid = torch.zeros(128, dtype=torch.uint8)
@@ -378,7 +381,7 @@ class PipelineWorkload:
 def make_workload(args, m, torch, device):
     rank, world, _ = dist_env()
     if args.workload == "pipeline":
-        return PipelineWorkload(m, torch, device, args.batch, rank, world)
+        return PipelineWorkload(m, torch, device, args.batch, rank, world, precise_masks=args.precise_masks)
     return CustomLayersWorkload(m, torch, device, args.batch, 0)
 
 
@@ -510,6 +513,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=[None, "pipeline", "custom_layers"])
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step (configs[1]: 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precise-masks", type=int, default=0, help="1: 2-term fp16 activations in the mask head (mrcnn_config.precise_masks)")
     args = ap.parse_args()
     if args.workload is None:
         args.workload = "pipeline"

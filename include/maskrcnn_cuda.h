@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define MRCNN_ABI_VERSION 1
+#define MRCNN_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MRCNN_API __attribute__((visibility("default")))
@@ -76,6 +76,7 @@ typedef struct mrcnn_ctx mrcnn_ctx;
  *   main_model_path        the MaskRCNN model bundle (ViewController.swift:37)
  *   classifier_model_path  MaskRCNNConfig.swift:16  (compiledClassifierModelURL)
  *   mask_model_path        MaskRCNNConfig.swift:17  (compiledMaskModelURL)
+ *   precise_masks          (no reference counterpart) numerical mode of the mask head, see the field
  * Paths may be NULL: the layer-level calls that do not need them still work
  * (proposal needs anchors; classifier/mask/predict need weights).
  */
@@ -97,6 +98,8 @@ typedef struct mrcnn_config {
   float detection_nms_iou;
   float mean_rgb[3];
   int32_t max_batch; /* images per predict() call the workspace is sized for */
+  int32_t precise_masks; /* 0: fp16 activations in the mask head (masks within 5e-4 of an fp32 evaluation);
+                            1: 2-term (hi, lo) fp16 activations, ~2x the mask-head tensor work (masks within 1e-4) */
   const char* anchors_path;
   const char* main_model_path;
   const char* classifier_model_path;

@@ -34,7 +34,7 @@ class mrcnn_config(C.Structure):
         ("max_detections", C.c_int32), ("detection_min_score", C.c_float),
         ("detection_nms_iou", C.c_float),
         ("mean_rgb", C.c_float * 3),
-        ("max_batch", C.c_int32),
+        ("max_batch", C.c_int32), ("precise_masks", C.c_int32),
         ("anchors_path", C.c_char_p), ("main_model_path", C.c_char_p),
         ("classifier_model_path", C.c_char_p), ("mask_model_path", C.c_char_p),
     ]

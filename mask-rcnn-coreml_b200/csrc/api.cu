@@ -36,9 +36,10 @@ void mrcnn_config_default(mrcnn_config* c) {
   c->detection_nms_iou = 0.3f;                     // DetectionLayer.swift:61
   c->mean_rgb[0] = 123.7f; c->mean_rgb[1] = 116.8f; c->mean_rgb[2] = 103.9f;  // Conversion/task.py:73-75
   c->max_batch = 8;
+  c->precise_masks = 0;
 }
 
-const char* mrcnn_version(void) { return "maskrcnn_cuda 0.1 (sm_100a, abi 1)"; }
+const char* mrcnn_version(void) { return "maskrcnn_cuda 0.2 (sm_100a, abi 2)"; }
 
 const char* mrcnn_last_error(const mrcnn_ctx* ctx) {
   if (ctx) return ctx->err.c_str();

@@ -60,6 +60,8 @@ struct ConvGemmParams {
   int ctas;                    // 1 or 2 (CTA pair / cta_group::2), must match the kernel instantiation and the cluster launch
   int nstages;                 // depth of the operand ring (A+B tiles), chosen per layer by the host
   int nbuf_log2;               // log2 of the number of 16 KB output / residual staging buffers (1 or 2)
+  int split_out;               // 1: outputs written as fp16 (hi, lo) pairs: channels [0,cout) = hi, [cout,2cout) = lo (2-term activations)
+  int md_precise;              // maskdot: keep the activation in fp32 (no fp16 rounding before the class dot product)
   int maskdot;                 // 1: mask-head tail fused into the deconv epilogue (see epilogue_maskdot)
   const int32_t* md_valid;     // [n_img] slot is a real detection
   const int32_t* md_cls;       // [n_img] class id of the slot
@@ -416,6 +418,101 @@ __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, const C
   if (e0) bulk_wait<0>();
 }
 
+// ---- 2-term ("split") outputs for the precise mask head: every activation v is stored as hi = fp16(v) and
+// lo = fp16(v - hi) in channels [n] and [cout + n] of a 2*cout-channel tensor.  The next layer sees 2*cout input
+// channels with its weights duplicated, so hi*w + lo*w accumulates in fp32: activations carry ~22 mantissa bits
+// through the tensor cores.  Same staging / TMA-store scheme as epilogue_staged (4 staging buffers: a hi/lo pair
+// per chunk, two pairs in rotation); no residual.
+template <int BN>
+__device__ __forceinline__ void epilogue_split(const ConvGemmParams& p, const CUtensorMap* tmC, uint8_t* out_gen, uint32_t out_base,
+                                               float* bias_gen, uint32_t tfull0, uint32_t tempty0, uint32_t tmem_base,
+                                               const TileSched ts, int warp, int lane) {
+  constexpr int kStageBytes = CG_BM * 64 * 2;
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+  const bool e0 = (threadIdx.x == 64);
+  const int nchunks = (min(BN, p.cout) + 63) / 64;
+  const float lo_clamp = p.relu ? 0.0f : -INFINITY;
+  uint32_t cc = 0;
+  int bias_n0 = -1;
+  int acc = 0; uint32_t acc_phase = 0;
+  if (e0) prefetch_tmap(tmC);
+  const uint32_t row_off = (uint32_t)row * 128u;
+  const uint32_t sw = (uint32_t)(row & 7);
+  for (int tile = ts.first; tile < ts.total; tile += ts.step) {
+    int n0, x0, y0, img;
+    ts.coords(p, BN, tile, n0, x0, y0, img);
+    if (n0 != bias_n0) {
+      epi_bar_sync();
+      for (int i = threadIdx.x - 64; i < BN; i += 128)
+        bias_gen[i] = (p.bias && n0 + i < p.cout) ? __ldg(p.bias + n0 + i) : 0.0f;
+      bias_n0 = n0;
+      epi_bar_sync();
+    }
+    mbar_wait(tfull0 + 8u * acc, acc_phase);
+    tc_fence_after();
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+    #pragma unroll 1
+    for (int c = 0; c < nchunks; ++c, ++cc) {
+      const uint32_t pair = (cc & 1u) * 2u;                    // staging buffers {0,1} / {2,3}
+      uint8_t* srow_hi = out_gen + pair * kStageBytes + row_off;
+      uint8_t* srow_lo = srow_hi + kStageBytes;
+      const int nc = n0 + c * 64;
+      epi_bar_sync();                                           // e0 has seen the stores that last read this pair finish
+      #pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[32];
+        tmem_ld32(t_addr + (uint32_t)(c * 64 + hh * 32), v);
+        float4 bq[8];
+        #pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4* bp = reinterpret_cast<const float4*>(bias_gen + (c * 64 + hh * 32 + g * 8));
+          bq[2 * g] = bp[0]; bq[2 * g + 1] = bp[1];
+        }
+        tmem_ld_wait();
+        #pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+          #pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
+          f[0] += bq[2 * g].x; f[1] += bq[2 * g].y; f[2] += bq[2 * g].z; f[3] += bq[2 * g].w;
+          f[4] += bq[2 * g + 1].x; f[5] += bq[2 * g + 1].y; f[6] += bq[2 * g + 1].z; f[7] += bq[2 * g + 1].w;
+          uint4 hv, lv;
+          __half2* hh2 = reinterpret_cast<__half2*>(&hv);
+          __half2* lh2 = reinterpret_cast<__half2*>(&lv);
+          #pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = fmaxf(f[2 * e], lo_clamp), b = fmaxf(f[2 * e + 1], lo_clamp);
+            const __half2 h = __floats2half2_rn(a, b);
+            const float2 hf = __half22float2(h);
+            hh2[e] = h;
+            lh2[e] = __floats2half2_rn(a - hf.x, b - hf.y);
+          }
+          const uint32_t off = (((uint32_t)(hh * 4 + g)) ^ sw) << 4;
+          *reinterpret_cast<uint4*>(srow_hi + off) = hv;
+          *reinterpret_cast<uint4*>(srow_lo + off) = lv;
+        }
+      }
+      if (c == nchunks - 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tempty_arrive(ts, tempty0 + 8u * acc);
+      }
+      fence_proxy_async_smem();
+      epi_bar_sync();
+      if (e0) {
+        const uint32_t sbuf = out_base + pair * (uint32_t)kStageBytes;
+        tma_store_4d(tmC, sbuf, nc, x0, y0, img);
+        tma_store_4d(tmC, sbuf + (uint32_t)kStageBytes, p.cout + nc, x0, y0, img);
+        bulk_commit();
+        bulk_wait_read<1>();                                    // the group that used the other pair has been read
+      }
+    }
+    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+  }
+  if (e0) bulk_wait<0>();
+}
+
 // ---- mask-head tail fused into the 2x2 stride-2 transposed convolution (TimeDistributedMaskLayer.swift:58-89):
 // N tile nt = sub-pixel (dy,dx) with all deconv_c channels; per output pixel
 //   m = sigmoid(b[cls] + sum_c fp16(relu(acc[c] + bias[c])) * w[cls][c])
@@ -462,10 +559,12 @@ __device__ __forceinline__ void epilogue_maskdot(const ConvGemmParams& p, float*
       tmem_ld_wait();
       #pragma unroll
       for (int g = 0; g < 8; ++g) {
-        const float a0 = __half2float(__float2half_rn(fmaxf(__uint_as_float(v[4 * g + 0]) + bq[g].x, 0.0f)));
-        const float a1 = __half2float(__float2half_rn(fmaxf(__uint_as_float(v[4 * g + 1]) + bq[g].y, 0.0f)));
-        const float a2 = __half2float(__float2half_rn(fmaxf(__uint_as_float(v[4 * g + 2]) + bq[g].z, 0.0f)));
-        const float a3 = __half2float(__float2half_rn(fmaxf(__uint_as_float(v[4 * g + 3]) + bq[g].w, 0.0f)));
+        float a0 = fmaxf(__uint_as_float(v[4 * g + 0]) + bq[g].x, 0.0f), a1 = fmaxf(__uint_as_float(v[4 * g + 1]) + bq[g].y, 0.0f);
+        float a2 = fmaxf(__uint_as_float(v[4 * g + 2]) + bq[g].z, 0.0f), a3 = fmaxf(__uint_as_float(v[4 * g + 3]) + bq[g].w, 0.0f);
+        if (!p.md_precise) {               // the unfused graph stores this activation as fp16
+          a0 = __half2float(__float2half_rn(a0)); a1 = __half2float(__float2half_rn(a1));
+          a2 = __half2float(__float2half_rn(a2)); a3 = __half2float(__float2half_rn(a3));
+        }
         dot = fmaf(a0, wq[g].x, dot); dot = fmaf(a1, wq[g].y, dot); dot = fmaf(a2, wq[g].z, dot); dot = fmaf(a3, wq[g].w, dot);
       }
     }
@@ -617,6 +716,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.maskdot) {
       float* bias_gen = reinterpret_cast<float*>(smem_gen + ring_bytes);       // bias + class weights live in the (unused) staging area
       cg::epilogue_maskdot<BN>(p, bias_gen, tfull_bar(0), tempty_bar(0), tmem_base, ts, warp, lane);
+    } else if (p.split_out) {
+      uint8_t* out_gen = smem_gen + ring_bytes;
+      float* bias_gen = reinterpret_cast<float*>(out_gen + out_bytes + 256);
+      cg::epilogue_split<BN>(p, &tmC, out_gen, out_base, bias_gen, tfull_bar(0), tempty_bar(0), tmem_base, ts, warp, lane);
     } else if (p.tma_out) {
       const uint32_t rf0 = rfull_bar(0), tf0 = tfull_bar(0), te0 = tempty_bar(0);
       uint8_t* out_gen = smem_gen + ring_bytes;

@@ -80,7 +80,7 @@ int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan) {
   p.w_out = L.w_out ? L.w_out : (L.w_in + 2 * L.pad - L.kw) / L.stride + 1;
   MRCNN_REQUIRE(ctx, p.h_out >= 1 && p.w_out >= 1, "conv: empty output");
   p.cout = L.cout;
-  p.ldc = L.ldc ? L.ldc : ((L.deconv ? L.deconv_c : L.cout) + 7) / 8 * 8;
+  p.ldc = L.ldc ? L.ldc : (L.split_out ? 2 * L.cout : ((L.deconv ? L.deconv_c : L.cout) + 7) / 8 * 8);
   MRCNN_REQUIRE(ctx, p.ldc % 8 == 0, "conv: ldc must be a multiple of 8");
   p.cin = L.cin;
   p.ntaps = ntaps;
@@ -171,6 +171,13 @@ int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan) {
   p.tma_out = (!L.no_tma_epilogue && !L.out_f32 && !L.deconv && (L.cout % 64) == 0 && bn >= 64) ? 1 : 0;
   p.tma_res = (p.tma_out && p.res_mode == 1) ? 1 : 0;
   p.trace = L.trace;
+  p.split_out = L.split_out;
+  p.md_precise = L.md_precise;
+  if (L.split_out) {
+    MRCNN_REQUIRE(ctx, !L.out_f32 && !L.deconv && !L.residual && (L.cout % 64) == 0 && bn >= 64 && p.ldc == 2 * L.cout,
+                  "conv: split (hi, lo) outputs need an fp16 NHWC output of 2*cout channels, cout % 64 == 0, no residual");
+    p.tma_out = 0; p.tma_res = 0;
+  }
   p.maskdot = L.maskdot;
   if (L.maskdot) {
     MRCNN_REQUIRE(ctx, L.deconv && L.deconv_c == 256 && bn == 256 && L.bias && L.md_valid && L.md_cls && L.md_w && L.md_b && L.md_ncls > 0,
@@ -181,14 +188,14 @@ int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan) {
   // trade ring stages for staging buffers so that the residual is prefetched further ahead and more stores are in flight
   {
     const int nkb = ntaps * (L.cin / CG_BK);
-    const bool deep_staging = p.tma_out && (p.tma_res || nkb <= 4);
+    const bool deep_staging = (p.tma_out && (p.tma_res || nkb <= 4)) || p.split_out;   // split outputs use 4 staging buffers
     const int deep[2][4] = {{8, 8, 6, 4}, {8, 8, 8, 6}}, shrt[2][4] = {{6, 6, 5, 3}, {8, 8, 6, 5}};     // [ctas-1][BN = 32, 64, 128, 256]
     const int bi = bn == 32 ? 0 : (bn == 64 ? 1 : (bn == 128 ? 2 : 3));
     p.nstages = deep_staging ? shrt[ctas - 1][bi] : deep[ctas - 1][bi];
     p.nbuf_log2 = deep_staging ? 2 : 1;
   }
-  if (p.tma_out) {
-    cuuint64_t cdims[4] = {(cuuint64_t)L.cout, (cuuint64_t)p.w_out, (cuuint64_t)p.h_out, (cuuint64_t)L.n};
+  if (p.tma_out || p.split_out) {
+    cuuint64_t cdims[4] = {(cuuint64_t)(p.split_out ? 2 * L.cout : L.cout), (cuuint64_t)p.w_out, (cuuint64_t)p.h_out, (cuuint64_t)L.n};
     cuuint64_t cstr[3] = {(cuuint64_t)p.ldc * 2, (cuuint64_t)p.ldc * 2 * p.w_out, (cuuint64_t)p.ldc * 2 * p.w_out * p.h_out};
     cuuint32_t cbox[4] = {64, (cuuint32_t)p.tw, (cuuint32_t)p.th, 1};
     cuuint32_t ces[4] = {1, 1, 1, 1};

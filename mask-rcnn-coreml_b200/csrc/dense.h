@@ -37,6 +37,8 @@ struct ConvLaunch {
   const __half* md_w = nullptr;
   const float* md_b = nullptr;
   int md_ncls = 0;
+  int md_precise = 0;            // keep the deconv activation in fp32 inside the fused tail
+  int split_out = 0;             // write fp16 (hi, lo) pairs: out = [n,h,w,2*cout] (see cg::epilogue_split)
 };
 
 struct ConvPlan {

@@ -417,23 +417,52 @@ static int mask_graph(mrcnn_ctx* ctx, int64_t M, std::shared_ptr<Graph>* out_gra
   const int P = cfg.pool_size_mask;
   const int64_t cap = (int64_t)(cfg.max_batch > 1 ? cfg.max_batch : 1) * cfg.max_detections;
   const int64_t MM = M > cap ? M : cap;
+  const bool precise = cfg.precise_masks != 0;
+  const int act_c = precise ? 512 : 256;          // precise mode: activations as (hi, lo) fp16 pairs, 2*256 channels
   __half *pooled, *ma, *mb;
   int32_t *valid, *slot_valid, *slot_cls;
   TRY(get_buf(ctx, "pooled_mask", (size_t)MM * P * P * 256 * 2, (void**)&pooled));
-  TRY(get_buf(ctx, "mask_a", (size_t)MM * P * P * 256 * 2, (void**)&ma));
-  TRY(get_buf(ctx, "mask_b", (size_t)MM * P * P * 256 * 2, (void**)&mb));
+  TRY(get_buf(ctx, "mask_a", (size_t)MM * P * P * act_c * 2, (void**)&ma));
+  TRY(get_buf(ctx, "mask_b", (size_t)MM * P * P * act_c * 2, (void**)&mb));
   TRY(get_buf(ctx, "mask_valid", (size_t)MM * 4, (void**)&valid));
   TRY(get_buf(ctx, "mask_slot_valid", (size_t)MM * 4, (void**)&slot_valid));
   TRY(get_buf(ctx, "mask_slot_cls", (size_t)MM * 4, (void**)&slot_cls));
   auto g = std::make_shared<Graph>();
   const char* names[4] = {"mask.conv1", "mask.conv2", "mask.conv3", "mask.conv4"};
+  // precise mode: weights of the layers that consume (hi, lo) activations, duplicated along the input channels
+  // ([cout][kh][kw][cin] -> [cout][kh][kw][2*cin] = (w | w)), so that hi*w + lo*w accumulates in fp32
+  auto duplicated = [&](const char* bufname, const WTensor& w, int rows, const __half** out) -> int {
+    __half* d;
+    TRY(get_buf(ctx, bufname, (size_t)rows * 512 * 2, (void**)&d));
+    MRCNN_CUDA_TRY(ctx, cudaMemcpy2DAsync(d, 512 * 2, w.d, 256 * 2, 256 * 2, rows, cudaMemcpyDeviceToDevice, ctx->stream));
+    MRCNN_CUDA_TRY(ctx, cudaMemcpy2DAsync(d + 256, 512 * 2, w.d, 256 * 2, 256 * 2, rows, cudaMemcpyDeviceToDevice, ctx->stream));
+    *out = d;
+    return MRCNN_OK;
+  };
   const __half* x = pooled;
+  int xc = 256;
   for (int i = 0; i < 4; ++i) {
     __half* y = (i & 1) ? mb : ma;
-    ConvArgs A;
-    A.wname = names[i]; A.x = x; A.n = (int)M; A.h = P; A.w = P; A.cin = 256; A.cout = 256; A.k = 3; A.pad = 1; A.relu = 1; A.out = y;
-    TRY(add_conv(ctx, *g, 2, A));
+    if (!precise) {
+      ConvArgs A;
+      A.wname = names[i]; A.x = x; A.n = (int)M; A.h = P; A.w = P; A.cin = 256; A.cout = 256; A.k = 3; A.pad = 1; A.relu = 1; A.out = y;
+      TRY(add_conv(ctx, *g, 2, A));
+    } else {
+      WTensor w, b;
+      TRY(find_w(ctx, 2, std::string(names[i]) + ".w", 0, &w));
+      TRY(find_w(ctx, 2, std::string(names[i]) + ".b", 1, &b));
+      MRCNN_REQUIRE(ctx, w.dims[0] == 256 && w.dims[1] == 3 && w.dims[2] == 3 && w.dims[3] == 256, "mask.conv*.w must be [256,3,3,256]");
+      const __half* wd = (const __half*)w.d;
+      if (xc == 512) { char bn_[32]; snprintf(bn_, 32, "mask_wdup%d", i); TRY(duplicated(bn_, w, 256 * 9, &wd)); }
+      ConvLaunch L;
+      L.x = x; L.n = (int)M; L.h_in = P; L.w_in = P; L.cin = xc; L.w = wd; L.cout = 256; L.kh = 3; L.kw = 3; L.pad = 1;
+      L.bias = (const float*)b.d; L.relu = 1; L.out = y; L.split_out = 1;
+      auto plan = std::make_shared<ConvPlan>();
+      TRY(conv_plan_build(ctx, L, plan.get()));
+      g->push_back([plan](mrcnn_ctx* c) { return conv_plan_run(c, *plan); });
+    }
     x = y;
+    xc = act_c;
   }
   // 2x2 stride-2 transposed conv (GEMM with 4*256 outputs, one N tile per sub-pixel) + ReLU, with the final
   // class-selected 1x1 conv + sigmoid fused into its epilogue: the (M, 2P, 2P, 256) tensor is never materialised.
@@ -447,12 +476,14 @@ static int mask_graph(mrcnn_ctx* ctx, int64_t M, std::shared_ptr<Graph>* out_gra
   MRCNN_REQUIRE(ctx, wf.dims[0] == cfg.num_classes && wf.dims[3] == 256 && bf.dims[0] == cfg.num_classes,
                 "mask.final.w must be [num_classes,1,1,256]");
   {
+    const __half* wd = (const __half*)w.d;
+    if (precise) TRY(duplicated("mask_wdup_deconv", w, 1024, &wd));
     ConvLaunch L;
-    L.x = x; L.n = (int)M; L.h_in = P; L.w_in = P; L.cin = 256;
-    L.w = (const __half*)w.d; L.cout = 1024; L.kh = 1; L.kw = 1; L.bias = (const float*)b.d; L.relu = 1;
+    L.x = x; L.n = (int)M; L.h_in = P; L.w_in = P; L.cin = act_c;
+    L.w = wd; L.cout = 1024; L.kh = 1; L.kw = 1; L.bias = (const float*)b.d; L.relu = 1;
     L.deconv = 1; L.deconv_c = 256; L.out = slot_valid /* patched per call */; L.out_f32 = 1; L.ldc = 256; L.bn = 256;
     L.maskdot = 1; L.md_valid = slot_valid; L.md_cls = slot_cls; L.md_w = (const __half*)wf.d; L.md_b = (const float*)bf.d;
-    L.md_ncls = cfg.num_classes;
+    L.md_ncls = cfg.num_classes; L.md_precise = precise ? 1 : 0;
     auto plan = std::make_shared<ConvPlan>();
     TRY(conv_plan_build(ctx, L, plan.get()));
     plan->flops += 2.0 * M * 4 * P * P * 256.0;      // the fused class-selected 1x1

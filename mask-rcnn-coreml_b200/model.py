@@ -29,12 +29,13 @@ class MaskRCNNConfig:
         self.maxProposals = 1000                  # ProposalLayer.swift:61
         self.maxDetections = 100                  # DetectionLayer.swift:57
         self.maxBatch = 8
+        self.preciseMasks = False                 # 2-term fp16 activations in the mask head (masks within 1e-4 of fp32)
 
     def context_overrides(self):
         return dict(image_h=self.imageShape[0], image_w=self.imageShape[1],
                     architecture={"resnet101": 101, "resnet50": 50}[self.architecture],
                     num_classes=self.numClasses, pre_nms_max_proposals=self.preNMSMaxProposals,
-                    max_proposals=self.maxProposals, max_detections=self.maxDetections, max_batch=self.maxBatch,
+                    max_proposals=self.maxProposals, max_detections=self.maxDetections, max_batch=self.maxBatch, precise_masks=int(self.preciseMasks),
                     anchors_path=self.anchorsURL, main_model_path=self.modelURL,
                     classifier_model_path=self.compiledClassifierModelURL, mask_model_path=self.compiledMaskModelURL)
 

@@ -165,3 +165,36 @@ def test_missing_weights_fail_loudly(pkg):
     with pytest.raises(pkg.MaskRCNNError):
         c.set_weights(0, b"garbage-not-a-blob-------------------")
     c.close()
+
+
+def test_mask_head_precise_mode_within_1e4_of_fp32(pkg, small):
+    """precise_masks = 1: 2-term (hi, lo) fp16 activations through the tensor cores; the mask head then matches a PURE
+    fp32 evaluation within the north star's 1e-4 (the default fp16-activation mode is within 5e-4)."""
+    from oracle.dense_ref import Ref
+    cfg = pkg.MaskRCNNConfig()
+    cfg.architecture, cfg.imageShape, cfg.preNMSMaxProposals, cfg.maxProposals, cfg.maxBatch = "resnet50", (SIZE, SIZE, 3), 1000, 200, 2
+    cfg.preciseMasks = True
+    _, blobs = pkg.weights.synthetic_blobs(50)
+    model = pkg.MaskRCNN(cfg, blobs=blobs, anchors=small["anchors"])
+    rng = np.random.default_rng(6)
+    d = 100
+    pooled = rng.standard_normal((1, d, 256, 14, 14)).astype(np.float16).astype(np.float32)
+    pooled[0, 70:] = 0.0
+    det = np.zeros((1, d, 6), np.float32)
+    det[0, :70, 4] = rng.integers(1, 81, 70)
+    det[0, :70, 5] = 0.9
+    out = np.full((1, d, 28, 28), 7.0, np.float32)
+    pkg.TimeDistributedMaskLayer(context=model.ctx).evaluate([pooled, det], [out])
+    ref = Ref(small["folded"], 50, act_half=False).mask(pooled[0, :70].transpose(0, 2, 3, 1)).cpu().numpy()
+    want = ref[np.arange(70), det[0, :70, 4].astype(int)]
+    err = np.abs(out[0, :70] - want).max()
+    assert err < 1e-4, err
+    assert not out[0, 70:].any()
+    # the whole pipeline runs in this mode too and keeps its invariants
+    dets, masks = model.prediction_batch(small["img"])
+    n = int((dets[0, :, 5] > 0).sum())
+    assert n > 0 and ((masks[0, :n] > 0) & (masks[0, :n] < 1)).all() and (masks[0, n:] == 0).all()
+    d0, m0 = small["model"].prediction_batch(small["img"])
+    np.testing.assert_array_equal(dets, d0)                       # detections do not depend on the mask mode
+    assert np.abs(masks - m0).max() < 2e-3
+    model.close()
