@@ -28,6 +28,7 @@ public class MaskRCNNConfig {
     public var maxProposals: Int32 = 1000
     public var maxDetections: Int32 = 100
     public var maxBatch: Int32 = 8
+    public var preciseMasks = false                 // mrcnn_config.precise_masks: 2-term fp16 activations in the mask head
 }
 
 public struct Detection {
@@ -54,6 +55,7 @@ public final class MaskRCNN {
         cfg.max_proposals = configuration.maxProposals
         cfg.max_detections = configuration.maxDetections
         cfg.max_batch = configuration.maxBatch
+        cfg.precise_masks = configuration.preciseMasks ? 1 : 0
         maxDetections = Int(cfg.max_detections)
         maskSize = 2 * Int(cfg.pool_size_mask)
         imageBytes = Int(cfg.image_h) * Int(cfg.image_w) * 3
