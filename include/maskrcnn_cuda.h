@@ -253,6 +253,23 @@ MRCNN_API int mrcnn_comm_init(mrcnn_ctx* ctx, const void* nccl_unique_id_128, in
 MRCNN_API int mrcnn_predict_allgather(mrcnn_ctx* ctx, int batch_local, const uint8_t* rgb,
                             float* detections_all, float* masks_all);
 
+/* ---- Streaming prediction: the same pipeline with two batches in flight, so that the host->device copy of batch
+ * i+1 (own copy stream) overlaps the compute of batch i and the caller prepares the next batch while the GPU
+ * works.  The reference predicts image after image from a loop (EvaluateCommand.swift:166-194); this is that loop
+ * with the copies taken off the critical path.
+ *   mrcnn_predict_submit  enqueues one batch and returns without waiting.  Arguments as mrcnn_predict (or, with
+ *                         MRCNN_SUBMIT_ALLGATHER, as mrcnn_predict_allgather).  Host buffers should be pinned and
+ *                         must stay valid, and untouched, until the matching mrcnn_predict_wait returns.
+ *                         MRCNN_EINVAL when two batches are already in flight.
+ *   mrcnn_predict_wait    blocks until the OLDEST submitted batch is complete (its outputs are then in the buffers
+ *                         that were passed to submit); results are bit-identical to mrcnn_predict.
+ *   mrcnn_predict_in_flight  number of submitted, not yet waited-for batches (0..2). */
+#define MRCNN_SUBMIT_ALLGATHER 1
+MRCNN_API int mrcnn_predict_submit(mrcnn_ctx* ctx, int batch, const uint8_t* rgb,
+                         float* detections, float* masks, int flags);
+MRCNN_API int mrcnn_predict_wait(mrcnn_ctx* ctx);
+MRCNN_API int mrcnn_predict_in_flight(const mrcnn_ctx* ctx);
+
 /* ---- Instrumentation (replaces the os_signpost intervals, e.g.
  * ProposalLayer.swift:105-194).  Per-stage device milliseconds of the last
  * mrcnn_predict, names in names_out (static strings), returns count. */
@@ -292,6 +309,10 @@ MRCNN_API int mrcnn_conv2d_nhwc_f16(mrcnn_ctx* ctx, const void* x, int n, int h,
 /* Debug: per-CTA event trace (clock64 stamps of the producer / MMA / epilogue roles) of the next
  * mrcnn_conv2d_nhwc_f16 calls; device buffer of 148 * 3 * (2*340 + 2) u64, NULL = off (tools/trace_conv.py). */
 MRCNN_API int mrcnn_debug_conv_trace(void* device_buffer);
+/* Debug: per-CTA stall statistics (clock64 totals per role) of the next chained ResNet-stage launches (conv_chain.cuh):
+ * after skipping `skip` chain launches, up to 8 launches write 148 x 16 u64 each into device_buffer; NULL = off
+ * (tools/chain_stats.py). */
+MRCNN_API int mrcnn_debug_chain_stats(void* device_buffer, int skip);
 /* Backbone + FPN + RPN only (stage-level parity hook; device pointers only):
  *   rgb [batch,H,W,3] u8 -> fmaps_out[l] [batch,H_l,W_l,256] f16 NHWC (P2..P5),
  *   probs_out [batch,N,2] f32, deltas_out [batch,N,4] f32. */

@@ -71,6 +71,9 @@ SIGNATURES = {
     "mrcnn_nccl_unique_id": (_i, [_vp]),
     "mrcnn_comm_init": (_i, [_vp, _vp, _i, _i]),
     "mrcnn_predict_allgather": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "mrcnn_predict_submit": (_i, [_vp, _i, _vp, _vp, _vp, _i]),
+    "mrcnn_predict_wait": (_i, [_vp]),
+    "mrcnn_predict_in_flight": (_i, [_vp]),
     "mrcnn_last_stage_times": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
     "mrcnn_launch_count": (_i64, [_vp]),
     "mrcnn_profile_enable": (_i, [_vp, _i]),
@@ -78,6 +81,7 @@ SIGNATURES = {
     "mrcnn_roialign_nhwc_f16": (_i, [_vp, _i, _vp, _i, _i64, C.POINTER(_vp), C.POINTER(C.c_int32), _i64, _i, _vp, _vp]),
     "mrcnn_conv2d_nhwc_f16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "mrcnn_debug_conv_trace": (_i, [_vp]),
+    "mrcnn_debug_chain_stats": (_i, [_vp, _i]),
     "mrcnn_backbone_eval": (_i, [_vp, _i, _vp, C.POINTER(_vp), _vp, _vp]),
 }
 

@@ -2,7 +2,9 @@
 // (dense.cu: tcgen05 implicit-GEMM convolution plans; pipeline.cu: the model).
 #pragma once
 #include "common.cuh"
+#include <string.h>
 #include "conv_gemm.cuh"
+#include "conv_chain.cuh"
 
 // One convolution (or GEMM) as the caller sees it.  Activations are NHWC fp16.
 struct ConvLaunch {
@@ -51,6 +53,25 @@ struct ConvPlan {
 
 int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan);
 int conv_plan_run(mrcnn_ctx* ctx, const ConvPlan& plan);
+
+// A sequence of convolutions as one persistent launch with image-granular dataflow between the layers
+// (conv_chain.cuh).  Dependencies are derived from the buffers: a layer depends on the chain layers that wrote its
+// input and its residual.
+struct ChainPlan {
+  ChainParams params;
+  CUtensorMap* d_maps = nullptr;     // [n_layers][4]
+  uint32_t* d_done = nullptr;        // [n_layers][flag_stride]
+  size_t done_bytes = 0;
+  int grid = 0;
+  double flops = 0;
+  ChainPlan() { memset(&params, 0, sizeof(params)); }
+  ~ChainPlan() { cudaFree(d_maps); cudaFree(d_done); }
+  ChainPlan(const ChainPlan&) = delete;
+  ChainPlan& operator=(const ChainPlan&) = delete;
+};
+// MRCNN_EINVAL (with a message) when a layer cannot run in a chain; the caller then launches the layers one by one.
+int chain_plan_build(mrcnn_ctx* ctx, const std::vector<ConvLaunch>& layers, ChainPlan* plan);
+int chain_plan_run(mrcnn_ctx* ctx, const ChainPlan& plan);
 
 int dense_load_weights(mrcnn_ctx* ctx, int which, const void* blob, size_t bytes);
 void dense_destroy(mrcnn_ctx* ctx);

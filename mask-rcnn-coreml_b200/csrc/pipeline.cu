@@ -19,6 +19,7 @@
 #include "aux_kernels.cuh"
 #include <dlfcn.h>
 #include <string.h>
+#include <algorithm>
 #include <functional>
 #include <memory>
 
@@ -47,6 +48,11 @@ struct DenseModel {
   cudaEvent_t ev[16] = {nullptr};
   int n_ev = 0;
   const char* ev_name[16] = {nullptr};
+  // ---- streaming prediction (mrcnn_predict_submit / mrcnn_predict_wait): two batches in flight ----
+  struct StreamSlot { cudaEvent_t h2d_done = nullptr, done = nullptr; };
+  StreamSlot slot[2];
+  cudaStream_t copy_stream = nullptr;   // H2D of batch i+1 runs here while batch i computes on ctx->stream
+  uint64_t submitted = 0, completed = 0;
 };
 
 static DenseModel* model_of(mrcnn_ctx* ctx) {
@@ -110,6 +116,11 @@ void dense_destroy(mrcnn_ctx* ctx) {
   for (auto& kv : m->bufs) cudaFree(kv.second.p);
   for (int i = 0; i < 3; ++i) cudaFree(m->ws[i].d_base);
   for (int i = 0; i < 16; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
+  for (int i = 0; i < 2; ++i) {
+    if (m->slot[i].h2d_done) cudaEventDestroy(m->slot[i].h2d_done);
+    if (m->slot[i].done) cudaEventDestroy(m->slot[i].done);
+  }
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   delete m;
   ctx->dense = nullptr;
 }
@@ -138,7 +149,7 @@ static int find_w(mrcnn_ctx* ctx, int which, const std::string& name, int dtype,
   return MRCNN_OK;
 }
 
-static int add_conv(mrcnn_ctx* ctx, Graph& g, int which, const ConvArgs& a) {
+static int make_conv_launch(mrcnn_ctx* ctx, int which, const ConvArgs& a, ConvLaunch* out) {
   WTensor w, b;
   int rc = find_w(ctx, which, std::string(a.wname) + ".w", 0, &w);
   if (rc) return rc;
@@ -157,10 +168,55 @@ static int add_conv(mrcnn_ctx* ctx, Graph& g, int which, const ConvArgs& a) {
   L.res_h = a.res_h; L.res_w = a.res_w; L.res_ld = a.res_ld;
   L.relu = a.relu; L.out_f32 = a.out_f32; L.out = a.out; L.ldc = a.ldc; L.bn = a.bn;
   if (a.deconv_c) { L.deconv = 1; L.deconv_c = a.deconv_c; }
+  *out = L;
+  return MRCNN_OK;
+}
+
+static int add_conv_launch(mrcnn_ctx* ctx, Graph& g, const ConvLaunch& L, const char* name) {
   auto plan = std::make_shared<ConvPlan>();
-  rc = conv_plan_build(ctx, L, plan.get());
-  if (rc) { ctx->err = std::string(a.wname) + ": " + ctx->err; return rc; }
+  int rc = conv_plan_build(ctx, L, plan.get());
+  if (rc) { ctx->err = std::string(name) + ": " + ctx->err; return rc; }
   g.push_back([plan](mrcnn_ctx* c) { return conv_plan_run(c, *plan); });
+  return MRCNN_OK;
+}
+
+static int add_conv(mrcnn_ctx* ctx, Graph& g, int which, const ConvArgs& a) {
+  ConvLaunch L;
+  int rc = make_conv_launch(ctx, which, a, &L);
+  if (rc) return rc;
+  return add_conv_launch(ctx, g, L, a.wname);
+}
+
+// A ResNet stage: one persistent chain launch (conv_chain.cuh) when every layer qualifies, else layer by layer.
+// MRCNN_CHAIN=0 switches chains off; MRCNN_CHAIN_STAGES is a bit mask of the stages (bit 0 = res2) that may chain.
+static int add_stage(mrcnn_ctx* ctx, Graph& g, int stage_index, const std::vector<ConvLaunch>& layers) {
+  const char* e = getenv("MRCNN_CHAIN");
+  const char* em = getenv("MRCNN_CHAIN_STAGES");
+  const bool chain_on = e ? atoi(e) != 0 : false;    // experimental: off unless MRCNN_CHAIN=1
+  const int stage_mask = em ? atoi(em) : 0xF;
+  if (chain_on && ((stage_mask >> stage_index) & 1) && layers.size() >= 2) {
+    const char* el = getenv("MRCNN_CHAIN_MAXLEN");        // experiment knob: split a stage into sub-chains of at most N layers
+    const size_t maxlen = el && atoi(el) > 0 ? (size_t)atoi(el) : (size_t)CH_MAX_LAYERS;
+    std::vector<std::shared_ptr<ChainPlan>> plans;
+    int rc = MRCNN_OK;
+    const std::string saved = ctx->err;
+    for (size_t i0 = 0; i0 < layers.size() && rc == MRCNN_OK; i0 += maxlen) {
+      const size_t i1 = std::min(layers.size(), i0 + maxlen);
+      auto plan = std::make_shared<ChainPlan>();
+      rc = chain_plan_build(ctx, std::vector<ConvLaunch>(layers.begin() + i0, layers.begin() + i1), plan.get());
+      plans.push_back(plan);
+    }
+    if (rc == MRCNN_OK) {
+      for (auto& plan : plans) g.push_back([plan](mrcnn_ctx* c) { return chain_plan_run(c, *plan); });
+      return MRCNN_OK;
+    }
+    if (rc != MRCNN_EINVAL) return rc;
+    ctx->err = saved;                      // not chainable (e.g. tiny maps): launch the layers one by one
+  }
+  for (const ConvLaunch& L : layers) {
+    int rc = add_conv_launch(ctx, g, L, "resnet stage layer");
+    if (rc) return rc;
+  }
   return MRCNN_OK;
 }
 
@@ -184,11 +240,17 @@ static int build_backbone(mrcnn_ctx* ctx, int B, std::shared_ptr<Graph>* out_gra
   const int H1 = H / 2, W1 = W / 2;                         // conv1 output
   const int H2 = H / 4, W2 = W / 4;                         // C2
   auto elems = [&](int h, int w, int c) { return (size_t)MB * h * w * c; };
-  __half *s2d, *a, *b, *t1, *t2, *sc, *c2, *c3, *c4, *c5;
+  __half *s2d, *a, *b, *pool, *t1, *t1b, *t2, *sc, *c2, *c3, *c4, *c5;
   TRY(get_buf(ctx, "s2d", elems(Hs, Ws, 16) * 2, (void**)&s2d));
   TRY(get_buf(ctx, "actA", elems(H1, W1, 64) * 2, (void**)&a));
   TRY(get_buf(ctx, "actB", elems(H2, W2, 256) * 2, (void**)&b));
+  // the max-pool output has its own buffer: inside a chained stage a ping-pong buffer may only ever be reused with the
+  // geometry of that stage (the per-image dependencies do not order accesses to differently laid out images)
+  TRY(get_buf(ctx, "pool", elems(H2, W2, 64) * 2, (void**)&pool));
   TRY(get_buf(ctx, "t1", elems(H2, W2, 64) * 2, (void**)&t1));
+  // second copy of the 2a output: inside a chained stage block k+1 may write its 2a tile while a neighbouring tile of
+  // block k's 3x3 convolution still reads the halo; alternating the buffer per block makes that safe (conv_chain.cuh)
+  TRY(get_buf(ctx, "t1b", elems(H2, W2, 64) * 2, (void**)&t1b));
   TRY(get_buf(ctx, "t2", elems(H2, W2, 64) * 2, (void**)&t2));
   TRY(get_buf(ctx, "sc", elems(H2, W2, 256) * 2, (void**)&sc));
   TRY(get_buf(ctx, "c2", elems(H2, W2, 256) * 2, (void**)&c2));
@@ -224,23 +286,31 @@ static int build_backbone(mrcnn_ctx* ctx, int B, std::shared_ptr<Graph>* out_gra
     plan->flops = 2.0 * B * H1 * W1 * 64.0 * 147.0;        // useful flops (the zero-padded taps do not count)
     g->push_back([plan](mrcnn_ctx* c) { return conv_plan_run(c, *plan); });
   }
-  // ---- max pool 3x3/2 -> [B, H2, W2, 64] in actB
+  // ---- max pool 3x3/2 -> [B, H2, W2, 64]
   g->push_back([=](mrcnn_ctx* c) -> int {
     ProfScope ps(c, PROF_GLUE, (double)B * (H1 * W1 + H2 * W2) * 128.0);
-    maxpool3x3s2_kernel<<<grid1d((int64_t)B * H2 * W2 * 8, 256), 256, 0, c->stream>>>(a, B, H1, W1, 64, H2, W2, b);
+    maxpool3x3s2_kernel<<<grid1d((int64_t)B * H2 * W2 * 8, 256), 256, 0, c->stream>>>(a, B, H1, W1, 64, H2, W2, pool);
     MRCNN_LAUNCH_CHECK(c);
     return MRCNN_OK;
   });
   // ---- residual stages
   const int nblocks101[4] = {3, 4, 23, 3}, nblocks50[4] = {3, 4, 6, 3};
   const int* nb = cfg.architecture == 101 ? nblocks101 : nblocks50;
-  __half* x = b;            // current block input
+  __half* x = pool;         // current block input
   __half* pp[2] = {a, b};   // ping-pong block outputs (a is free again after the max pool)
   int cur = 1;              // x lives in pp[cur]
   int h = H2, w = W2, cin = 64;
   __half* stage_out[4] = {c2, c3, c4, c5};
   for (int s = 0; s < 4; ++s) {
     const int f = 64 << s;
+    std::vector<ConvLaunch> stage_layers;
+    auto stage_conv = [&](const ConvArgs& ca) -> int {
+      ConvLaunch L;
+      int rc = make_conv_launch(ctx, 0, ca, &L);
+      if (rc) return rc;
+      stage_layers.push_back(L);
+      return MRCNN_OK;
+    };
     for (int i = 0; i < nb[s]; ++i) {
       const int stride = (i == 0 && s > 0) ? 2 : 1;
       const int ho = h / stride, wo = w / stride;
@@ -249,25 +319,26 @@ static int build_backbone(mrcnn_ctx* ctx, int B, std::shared_ptr<Graph>* out_gra
       snprintf(n2c, 64, "res%d.%d.2c", s + 2, i); snprintf(n1, 64, "res%d.%d.1", s + 2, i);
       __half* y = (i == nb[s] - 1) ? stage_out[s] : pp[cur ^ 1];
       ConvArgs A;
-      A.wname = n2a; A.x = x; A.n = B; A.h = h; A.w = w; A.cin = cin; A.cout = f; A.k = 1; A.stride = stride; A.relu = 1; A.out = t1;
-      TRY(add_conv(ctx, *g, 0, A));
+      A.wname = n2a; A.x = x; A.n = B; A.h = h; A.w = w; A.cin = cin; A.cout = f; A.k = 1; A.stride = stride; A.relu = 1; A.out = (i & 1) ? t1b : t1;
+      TRY(stage_conv(A));
       ConvArgs Bc;
-      Bc.wname = n2b; Bc.x = t1; Bc.n = B; Bc.h = ho; Bc.w = wo; Bc.cin = f; Bc.cout = f; Bc.k = 3; Bc.pad = 1; Bc.relu = 1; Bc.out = t2;
-      TRY(add_conv(ctx, *g, 0, Bc));
+      Bc.wname = n2b; Bc.x = (i & 1) ? t1b : t1; Bc.n = B; Bc.h = ho; Bc.w = wo; Bc.cin = f; Bc.cout = f; Bc.k = 3; Bc.pad = 1; Bc.relu = 1; Bc.out = t2;
+      TRY(stage_conv(Bc));
       const __half* res = x;
       if (i == 0) {
         ConvArgs S;
         S.wname = n1; S.x = x; S.n = B; S.h = h; S.w = w; S.cin = cin; S.cout = 4 * f; S.k = 1; S.stride = stride; S.out = sc;
-        TRY(add_conv(ctx, *g, 0, S));
+        TRY(stage_conv(S));
         res = sc;
       }
       ConvArgs Cc;
       Cc.wname = n2c; Cc.x = t2; Cc.n = B; Cc.h = ho; Cc.w = wo; Cc.cin = f; Cc.cout = 4 * f; Cc.k = 1; Cc.relu = 1;
       Cc.res = res; Cc.res_mode = 1; Cc.out = y;
-      TRY(add_conv(ctx, *g, 0, Cc));
+      TRY(stage_conv(Cc));
       if (y == pp[cur ^ 1]) cur ^= 1;
       x = y; h = ho; w = wo; cin = 4 * f;
     }
+    TRY(add_stage(ctx, *g, s, stage_layers));
   }
   // ---- FPN
   const int lh[5] = {H2, H2 / 2, H2 / 4, H2 / 8, H2 / 16}, lw[5] = {W2, W2 / 2, W2 / 4, W2 / 8, W2 / 16};
@@ -650,6 +721,43 @@ __global__ void unpack_rows_kernel(const float* __restrict__ packed, int n_det, 
   }
 }
 
+static int allgather_reserve(mrcnn_ctx* ctx, int batch_local) {
+  const mrcnn_config& cfg = ctx->cfg;
+  const int D = cfg.max_detections, S = 2 * cfg.pool_size_mask;
+  const int n_det = D * 6, n_mask = D * S * S, row = n_det + n_mask;
+  const int total = batch_local * ctx->nranks;
+  void* t;
+  TRY(get_buf(ctx, "ag_det", sizeof(float) * n_det * batch_local, &t));
+  TRY(get_buf(ctx, "ag_mask", sizeof(float) * (size_t)n_mask * batch_local, &t));
+  TRY(get_buf(ctx, "ag_send", sizeof(float) * (size_t)row * batch_local, &t));
+  TRY(get_buf(ctx, "ag_recv", sizeof(float) * (size_t)row * total, &t));
+  return MRCNN_OK;
+}
+
+// predict on this rank's images, then the one exchange step of the path: a single all-gather of the packed rows over
+// NVLink.  Device pointers; buffers reserved by allgather_reserve.
+static int predict_allgather_device(mrcnn_ctx* ctx, int batch_local, const uint8_t* drgb, float* ddet_all, float* dmask_all) {
+  DenseModel* m = model_of(ctx);
+  const mrcnn_config& cfg = ctx->cfg;
+  const int D = cfg.max_detections, S = 2 * cfg.pool_size_mask;
+  const int n_det = D * 6, n_mask = D * S * S, row = n_det + n_mask;
+  const int total = batch_local * ctx->nranks;
+  float* ldet = (float*)m->bufs["ag_det"].p; float* lmask = (float*)m->bufs["ag_mask"].p;
+  float* send = (float*)m->bufs["ag_send"].p; float* recv = (float*)m->bufs["ag_recv"].p;
+  TRY(predict_device(ctx, batch_local, drgb, ldet, lmask));
+  {
+    ProfScope ps(ctx, PROF_GLUE, (double)row * 4.0 * (batch_local * 2 + total * 2));
+    pack_rows_kernel<<<dim3(32, batch_local), 256, 0, ctx->stream>>>(ldet, lmask, n_det, n_mask, send);
+    MRCNN_LAUNCH_CHECK(ctx);
+    int r = g_nccl.AllGather(send, recv, (size_t)row * batch_local, /*ncclFloat*/ 7, ctx->nccl_comm, ctx->stream);
+    if (r != 0) return nccl_fail(ctx, "ncclAllGather", r);
+    unpack_rows_kernel<<<dim3(32, total), 256, 0, ctx->stream>>>(recv, n_det, n_mask, ddet_all, dmask_all);
+    MRCNN_LAUNCH_CHECK(ctx);
+  }
+  stage_mark(ctx, "AllGather");
+  return MRCNN_OK;
+}
+
 extern "C" {
 
 MRCNN_API int mrcnn_nccl_unique_id(void* id_out_128) {
@@ -780,32 +888,89 @@ MRCNN_API int mrcnn_predict_allgather(mrcnn_ctx* ctx, int batch_local, const uin
   cudaSetDevice(ctx->device);
   const mrcnn_config& cfg = ctx->cfg;
   const int D = cfg.max_detections, S = 2 * cfg.pool_size_mask;
-  const int n_det = D * 6, n_mask = D * S * S, row = n_det + n_mask;
   const int total = batch_local * ctx->nranks;
-  float *ldet, *lmask, *send, *recv;
-  TRY(get_buf(ctx, "ag_det", sizeof(float) * n_det * batch_local, (void**)&ldet));
-  TRY(get_buf(ctx, "ag_mask", sizeof(float) * (size_t)n_mask * batch_local, (void**)&lmask));
-  TRY(get_buf(ctx, "ag_send", sizeof(float) * (size_t)row * batch_local, (void**)&send));
-  TRY(get_buf(ctx, "ag_recv", sizeof(float) * (size_t)row * total, (void**)&recv));
+  TRY(allgather_reserve(ctx, batch_local));
   Stager st(ctx);
   int rc = MRCNN_OK;
   const uint8_t* drgb = (const uint8_t*)st.in(rgb, (size_t)batch_local * cfg.image_h * cfg.image_w * 3, &rc);
-  float* ddet = (float*)st.out(detections_all, sizeof(float) * n_det * total, &rc);
-  float* dmask = (float*)st.out(masks_all, sizeof(float) * (size_t)n_mask * total, &rc);
+  float* ddet = (float*)st.out(detections_all, sizeof(float) * 6 * D * total, &rc);
+  float* dmask = (float*)st.out(masks_all, sizeof(float) * (size_t)S * S * D * total, &rc);
   if (rc) return mrcnn_fail(ctx, rc, "predict_allgather: staging failed");
-  TRY(predict_device(ctx, batch_local, drgb, ldet, lmask));
-  {
-    ProfScope ps(ctx, PROF_GLUE, (double)row * 4.0 * (batch_local * 2 + total * 2));
-    pack_rows_kernel<<<dim3(32, batch_local), 256, 0, ctx->stream>>>(ldet, lmask, n_det, n_mask, send);
-    MRCNN_LAUNCH_CHECK(ctx);
-    // the one exchange step of the path: a single all-gather of the packed rows over NVLink
-    int r = g_nccl.AllGather(send, recv, (size_t)row * batch_local, /*ncclFloat*/ 7, ctx->nccl_comm, ctx->stream);
-    if (r != 0) return nccl_fail(ctx, "ncclAllGather", r);
-    unpack_rows_kernel<<<dim3(32, total), 256, 0, ctx->stream>>>(recv, n_det, n_mask, ddet, dmask);
-    MRCNN_LAUNCH_CHECK(ctx);
-  }
-  stage_mark(ctx, "AllGather");
+  TRY(predict_allgather_device(ctx, batch_local, drgb, ddet, dmask));
   return st.finish();
+}
+
+// ---- streaming prediction: at most two batches in flight ---------------------------------------
+MRCNN_API int mrcnn_predict_submit(mrcnn_ctx* ctx, int batch, const uint8_t* rgb, float* detections, float* masks, int flags) {
+  if (!ctx) return MRCNN_EINVAL;
+  MRCNN_REQUIRE(ctx, rgb && detections && masks && batch >= 1, "predict_submit: bad argument");
+  MRCNN_REQUIRE(ctx, (flags & ~MRCNN_SUBMIT_ALLGATHER) == 0, "predict_submit: unknown flag");
+  const bool gather = (flags & MRCNN_SUBMIT_ALLGATHER) != 0;
+  if (gather) MRCNN_REQUIRE(ctx, ctx->nccl_comm, "predict_submit: MRCNN_SUBMIT_ALLGATHER needs mrcnn_comm_init first");
+  cudaSetDevice(ctx->device);
+  DenseModel* m = model_of(ctx);
+  MRCNN_REQUIRE(ctx, m->submitted - m->completed < 2, "predict_submit: two batches are already in flight; call mrcnn_predict_wait first");
+  const mrcnn_config& cfg = ctx->cfg;
+  const int D = cfg.max_detections, S = 2 * cfg.pool_size_mask;
+  const int total = gather ? batch * ctx->nranks : batch;
+  const int k = (int)(m->submitted & 1);
+  DenseModel::StreamSlot& sl = m->slot[k];
+  if (!m->copy_stream) MRCNN_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  if (!sl.done) {
+    MRCNN_CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+    MRCNN_CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  }
+  // Per-slot device mirrors of host arguments.  A slot is only reused after the batch that used it was waited for
+  // (the two-in-flight rule above), so nothing on the device still reads or writes them here.
+  const size_t in_bytes = (size_t)batch * cfg.image_h * cfg.image_w * 3;
+  const size_t det_bytes = sizeof(float) * 6 * D * total, mask_bytes = sizeof(float) * (size_t)S * S * D * total;
+  const char* nm_in[2] = {"stream_in0", "stream_in1"};
+  const char* nm_det[2] = {"stream_det0", "stream_det1"};
+  const char* nm_mask[2] = {"stream_mask0", "stream_mask1"};
+  const bool in_host = !Stager::is_device_ptr(rgb), det_host = !Stager::is_device_ptr(detections),
+             mask_host = !Stager::is_device_ptr(masks);
+  // every buffer the graphs and this call need exists before anything is enqueued (growing one synchronises)
+  {
+    const int MBs = cfg.max_batch > batch ? cfg.max_batch : batch;
+    void* tmp;
+    if (in_host) TRY(get_buf(ctx, nm_in[k], (size_t)MBs * cfg.image_h * cfg.image_w * 3, &tmp));
+    if (det_host) TRY(get_buf(ctx, nm_det[k], det_bytes, &tmp));
+    if (mask_host) TRY(get_buf(ctx, nm_mask[k], mask_bytes, &tmp));
+    if (gather) TRY(allgather_reserve(ctx, batch));
+  }
+  const uint8_t* drgb = rgb;
+  if (in_host) {
+    // the copy of this batch overlaps the compute of the previous one: own stream, then an event edge
+    drgb = (const uint8_t*)m->bufs[nm_in[k]].p;
+    MRCNN_CUDA_TRY(ctx, cudaMemcpyAsync((void*)drgb, rgb, in_bytes, cudaMemcpyHostToDevice, m->copy_stream));
+    MRCNN_CUDA_TRY(ctx, cudaEventRecord(sl.h2d_done, m->copy_stream));
+    MRCNN_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, sl.h2d_done, 0));
+  }
+  float* ddet = det_host ? (float*)m->bufs[nm_det[k]].p : detections;
+  float* dmask = mask_host ? (float*)m->bufs[nm_mask[k]].p : masks;
+  if (gather) TRY(predict_allgather_device(ctx, batch, drgb, ddet, dmask));
+  else TRY(predict_device(ctx, batch, drgb, ddet, dmask));
+  if (det_host) MRCNN_CUDA_TRY(ctx, cudaMemcpyAsync(detections, ddet, det_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (mask_host) MRCNN_CUDA_TRY(ctx, cudaMemcpyAsync(masks, dmask, mask_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  MRCNN_CUDA_TRY(ctx, cudaEventRecord(sl.done, ctx->stream));
+  m->submitted++;
+  return MRCNN_OK;
+}
+
+MRCNN_API int mrcnn_predict_wait(mrcnn_ctx* ctx) {
+  if (!ctx) return MRCNN_EINVAL;
+  cudaSetDevice(ctx->device);
+  DenseModel* m = model_of(ctx);
+  MRCNN_REQUIRE(ctx, m->completed < m->submitted, "predict_wait: nothing in flight");
+  const int k = (int)(m->completed & 1);
+  m->completed++;                   // the slot is released even when the wait reports an error
+  MRCNN_CUDA_TRY(ctx, cudaEventSynchronize(m->slot[k].done));
+  return MRCNN_OK;
+}
+
+MRCNN_API int mrcnn_predict_in_flight(const mrcnn_ctx* ctx) {
+  if (!ctx || !ctx->dense) return 0;
+  return (int)(ctx->dense->submitted - ctx->dense->completed);
 }
 
 }  // extern "C"

@@ -111,6 +111,42 @@ class MaskRCNN:
         check(self.ctx.handle, lib().mrcnn_predict(self.ctx.handle, b, ptr(images), ptr(detections), ptr(masks)))
         return detections, masks
 
+    # ---- streaming: two batches in flight (mrcnn_predict_submit / mrcnn_predict_wait) ----
+    def submit(self, images, detections, masks, allgather=False):
+        """Enqueues one batch and returns at once; the host->device copy overlaps the previous batch's compute.
+        Host buffers should be pinned and must stay untouched until the matching wait() returns.  With
+        allgather=True the outputs hold every rank's results (mrcnn_predict_allgather semantics)."""
+        b = images.shape[0]
+        if tuple(images.shape[1:]) != self.shape:
+            raise _cabi.MaskRCNNError(_cabi.EINVAL, f"images must be [B,{self.shape[0]},{self.shape[1]},3] uint8")
+        flags = 1 if allgather else 0          # MRCNN_SUBMIT_ALLGATHER
+        check(self.ctx.handle, lib().mrcnn_predict_submit(self.ctx.handle, b, ptr(images), ptr(detections), ptr(masks), flags))
+
+    def wait(self):
+        """Blocks until the oldest submitted batch is complete (outputs are in the buffers given to submit)."""
+        check(self.ctx.handle, lib().mrcnn_predict_wait(self.ctx.handle))
+
+    @property
+    def in_flight(self):
+        return int(lib().mrcnn_predict_in_flight(self.ctx.handle))
+
+    def prediction_stream(self, batches):
+        """Iterator of image batches -> iterator of (detections, masks), in order, keeping two batches in flight:
+        the loop of EvaluateCommand.swift:166-194 with the copies off the critical path."""
+        pending = []
+        for images in batches:
+            b = images.shape[0]
+            det = np.empty((b, self.D, 6), np.float32)
+            msk = np.empty((b, self.D, self.S, self.S), np.float32)
+            if len(pending) == 2:
+                self.wait()
+                yield pending.pop(0)[1:]
+            self.submit(images, det, msk)
+            pending.append((images, det, msk))      # keeps the input alive until its wait
+        while pending:
+            self.wait()
+            yield pending.pop(0)[1:]
+
     def prediction(self, image):
         """One image -> {"detections": (D,6), "mask": (D,S,S)} like MaskRCNNOutput."""
         d, m = self.prediction_batch(np.ascontiguousarray(image)[None])

@@ -198,3 +198,88 @@ def test_mask_head_precise_mode_within_1e4_of_fp32(pkg, small):
     np.testing.assert_array_equal(dets, d0)                       # detections do not depend on the mask mode
     assert np.abs(masks - m0).max() < 2e-3
     model.close()
+
+
+def test_streaming_submit_wait_bit_identical_to_predict(pkg, small):
+    """mrcnn_predict_submit / mrcnn_predict_wait (two batches in flight, H2D on the copy stream) returns, in order,
+    exactly what the blocking mrcnn_predict returns for the same batches; pinned, pageable and device buffers."""
+    import torch
+    m = small["model"]
+    rng = np.random.default_rng(77)
+    batches = [small["img"]] + [rng.integers(0, 256, small["img"].shape, dtype=np.uint8) for _ in range(4)]
+    want = [m.prediction_batch(b) for b in batches]
+    want = [(d.copy(), k.copy()) for d, k in want]
+    # (1) pageable numpy buffers through the iterator
+    got = list(m.prediction_stream(iter(batches)))
+    assert len(got) == len(batches) and m.in_flight == 0
+    for (d, k), (wd, wk) in zip(got, want):
+        np.testing.assert_array_equal(d, wd)
+        np.testing.assert_array_equal(k, wk)
+    # (2) pinned host tensors, explicit submit / wait with two in flight
+    pin = [torch.from_numpy(b).pin_memory() for b in batches]
+    dets = [torch.full((2, m.D, 6), -1.0).pin_memory() for _ in batches]
+    msks = [torch.full((2, m.D, m.S, m.S), -1.0).pin_memory() for _ in batches]
+    for i in range(len(batches)):
+        m.submit(pin[i], dets[i], msks[i])
+        if i >= 1:
+            m.wait()
+            np.testing.assert_array_equal(dets[i - 1].numpy(), want[i - 1][0])     # complete as soon as its wait returns
+    assert m.in_flight == 1
+    m.wait()
+    for i in range(len(batches)):
+        np.testing.assert_array_equal(dets[i].numpy(), want[i][0])
+        np.testing.assert_array_equal(msks[i].numpy(), want[i][1])
+    # (3) device buffers
+    dimg = torch.from_numpy(batches[2]).cuda()
+    ddet = torch.zeros((2, m.D, 6), device="cuda"); dmsk = torch.zeros((2, m.D, m.S, m.S), device="cuda")
+    m.submit(dimg, ddet, dmsk)
+    m.wait()
+    np.testing.assert_array_equal(ddet.cpu().numpy(), want[2][0])
+    np.testing.assert_array_equal(dmsk.cpu().numpy(), want[2][1])
+
+
+def test_streaming_misuse_fails_loudly(pkg, small):
+    import torch
+    m = small["model"]
+    with pytest.raises(pkg.MaskRCNNError, match="nothing in flight"):
+        m.wait()
+    img = torch.from_numpy(small["img"]).pin_memory()
+    bufs = [(torch.zeros((2, m.D, 6)).pin_memory(), torch.zeros((2, m.D, m.S, m.S)).pin_memory()) for _ in range(3)]
+    m.submit(img, *bufs[0]); m.submit(img, *bufs[1])
+    with pytest.raises(pkg.MaskRCNNError, match="already in flight"):
+        m.submit(img, *bufs[2])
+    with pytest.raises(pkg.MaskRCNNError, match="comm_init"):
+        m.wait(); m.submit(img, *bufs[2], allgather=True)
+    m.wait()
+    assert m.in_flight == 0
+    np.testing.assert_array_equal(bufs[0][0].numpy(), bufs[1][0].numpy())
+
+
+def _model_with_env(pkg, monkeypatch, chain, arch=50, size=SIZE, batch=2, pre=1000, props=200):
+    monkeypatch.setenv("MRCNN_CHAIN", "1" if chain else "0")
+    _, blobs = pkg.weights.synthetic_blobs(arch)
+    cfg = pkg.MaskRCNNConfig()
+    cfg.architecture, cfg.imageShape = ("resnet50" if arch == 50 else "resnet101"), (size, size, 3)
+    cfg.preNMSMaxProposals, cfg.maxProposals, cfg.maxBatch = pre, props, batch
+    return pkg.MaskRCNN(cfg, blobs=blobs, anchors=pkg.synth.generate_anchors(size, size))
+
+
+@pytest.mark.parametrize("batch", [1, 2, 3])
+def test_chained_stages_bit_identical_to_layerwise_launches(pkg, small, monkeypatch, batch):
+    """The persistent per-stage chain kernel (conv_chain.cuh: all layers of a ResNet stage in one launch, image-granular
+    dataflow between layers) must reproduce the layer-by-layer launches bit for bit: feature maps, RPN outputs."""
+    rng = np.random.default_rng(batch)
+    img = rng.integers(0, 256, (batch, SIZE, SIZE, 3), dtype=np.uint8)
+    outs = []
+    for chain in (False, True):
+        model = _model_with_env(pkg, monkeypatch, chain, batch=batch)
+        try:
+            for _ in range(3):                                    # repeated runs: the flags are re-armed every launch
+                fm, probs, deltas = _backbone(pkg, model, img)
+            outs.append((fm, probs, deltas))
+        finally:
+            model.close()
+    for l in range(4):
+        np.testing.assert_array_equal(outs[0][0][l], outs[1][0][l])
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    np.testing.assert_array_equal(outs[0][2], outs[1][2])
