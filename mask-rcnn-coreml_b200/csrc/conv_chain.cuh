@@ -58,7 +58,7 @@
 #define CH_SMEM_BYTES (1024 + CH_STAGES * CH_STAGE_BYTES + CH_NBUF * CH_OUT_BYTES + 512)
 
 struct ChainLayer {               // 64 bytes, lives in the kernel parameter (constant bank)
-  uint32_t item_end;              // cumulative number of pair items up to and including this layer
+  uint32_t item_end_unused;
   uint16_t tiles_x, tiles_y, tiles_n, tiles_per_img;
   uint16_t cout, bn, cin_chunks;
   uint8_t ntaps, stride, tw, th, relu, res;
@@ -72,14 +72,29 @@ struct ChainLayer {               // 64 bytes, lives in the kernel parameter (co
 };
 static_assert(sizeof(ChainLayer) == 64, "ChainLayer must stay 64 bytes");
 
+// The work list is a sequence of segments.  A segment is either a run of consecutive items of one layer, or two such
+// runs (of different layers, over different images) zipped together: item i of a zipped segment belongs to stream X
+// iff floor((i+1)*nx/n) > floor(i*nx/n), n = nx + ny.  The host uses zipped segments to software-pipeline two halves of
+// the batch two layers apart, so that a pair alternates between MMA-heavy items (3x3 convolutions) and epilogue-heavy
+// ones (the 1x1 expansions with their residual) instead of running each kind back to back.
+#define CH_MAX_SEGS 224
+struct ChainSeg {                 // 24 bytes
+  uint32_t item_end;              // cumulative number of pair items up to and including this segment
+  int16_t lx, ly;                 // layers of the two streams (ly < 0: single stream)
+  uint32_t x0, y0;                // first item of each stream inside its layer
+  uint32_t nx, ny;                // items of each stream in this segment
+};
+
 struct ChainParams {
   int n_layers, n_img;
+  int n_segs;
   uint32_t total_items;
   int flag_stride;                // counters per layer (>= number of 128-pixel tiles of any layer)
   uint32_t* done;                 // [n_layers][flag_stride], zeroed before the launch
   const CUtensorMap* maps;        // [n_layers][4] = A, B, C, R (global memory, 64-byte aligned)
   unsigned long long* stats;      // debug: [gridDim.x][CH_NSTAT] clock totals per CTA (nullptr in production), see CH_STAT_*
   ChainLayer L[CH_MAX_LAYERS];
+  ChainSeg S[CH_MAX_SEGS];
 };
 
 #ifdef CONV_CHAIN_KERNEL      // the kernel itself is compiled in dense.cu only
@@ -108,17 +123,26 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
 // position of one CTA in the chain's item list
 struct ChainPos {
   uint32_t g;        // global item index
-  uint32_t base;     // first item of layer l
-  int l;
+  uint32_t sbase;    // first item of segment s
+  int s;             // segment
+  int l;             // layer of item g (set by seek)
+  uint32_t w;        // index of item g inside its layer (set by seek)
+  __device__ __forceinline__ void init(uint32_t g0) { g = g0; sbase = 0; s = 0; l = 0; w = 0; }
   __device__ __forceinline__ void seek(const ChainParams& cp) {
-    while (l < cp.n_layers - 1 && g >= cp.L[l].item_end) { base = cp.L[l].item_end; ++l; }
+    while (s < cp.n_segs - 1 && g >= cp.S[s].item_end) { sbase = cp.S[s].item_end; ++s; }
+    const ChainSeg& G = cp.S[s];
+    const uint32_t i = g - sbase;
+    if (G.ly < 0) { l = G.lx; w = G.x0 + i; return; }
+    const uint32_t n = G.nx + G.ny;
+    const uint32_t xa = (uint32_t)(((unsigned long long)i * G.nx) / n);             // X items before item i
+    const uint32_t xb = (uint32_t)(((unsigned long long)(i + 1u) * G.nx) / n);
+    if (xb > xa) { l = G.lx; w = G.x0 + xa; } else { l = G.ly; w = G.y0 + (i - xa); }
   }
   __device__ __forceinline__ void coords(const ChainParams& cp, int crank, int& n0, int& x0, int& y0, int& img) const {
     int mt; coords(cp, crank, n0, x0, y0, img, mt);
   }
   __device__ __forceinline__ void coords(const ChainParams& cp, int crank, int& n0, int& x0, int& y0, int& img, int& mt) const {
     const ChainLayer& L = cp.L[l];
-    const uint32_t w = g - base;
     const int nt = (int)(w % L.tiles_n);
     mt = (int)(w / L.tiles_n) * 2 + crank;
     n0 = nt * L.bn;
@@ -184,7 +208,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      cg::ChainPos pos; pos.g = pidx; pos.base = 0; pos.l = 0;
+      cg::ChainPos pos; pos.init(pidx);
       int cur_l = -1;
       uint32_t ord = 0;
       // Dependency counters are polled one item ahead: the loads for item k+1 are issued before the TMA copies of item
@@ -216,10 +240,14 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
         const ChainLayer& L = cp.L[pos.l];
         const CUtensorMap* tmA = cp.maps + 4 * pos.l;
         const CUtensorMap* tmB = tmA + 1;
-        if (pos.l != cur_l) {
+        if (pos.s != cur_l) {                               // new segment: fetch the descriptors of the next one ahead of time
           if (cur_l < 0) { cg::prefetch_tmap(tmA); cg::prefetch_tmap(tmB); }
-          if (pos.l + 1 < cp.n_layers) { cg::prefetch_tmap(tmA + 4); cg::prefetch_tmap(tmB + 4); }   // next layer's descriptors
-          cur_l = pos.l;
+          if (pos.s + 1 < cp.n_segs) {
+            const ChainSeg& NS = cp.S[pos.s + 1];
+            cg::prefetch_tmap(cp.maps + 4 * NS.lx); cg::prefetch_tmap(cp.maps + 4 * NS.lx + 1);
+            if (NS.ly >= 0) { cg::prefetch_tmap(cp.maps + 4 * NS.ly); cg::prefetch_tmap(cp.maps + 4 * NS.ly + 1); }
+          }
+          cur_l = pos.s;
         }
         int n0, px0, py0, img, mt;
         pos.coords(cp, (int)crank, n0, px0, py0, img, mt);
@@ -295,7 +323,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       unsigned long long acc_mf = 0, acc_mt = 0;
-      cg::ChainPos pos; pos.g = pidx; pos.base = 0; pos.l = 0;
+      cg::ChainPos pos; pos.init(pidx);
       for (; pos.g < cp.total_items; pos.g += npairs) {
         pos.seek(cp);
         const ChainLayer& L = cp.L[pos.l];
@@ -335,7 +363,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
     uint32_t rphase = 0;             // bit b = parity to wait for on res_full[b]
     int acc = 0; uint32_t acc_phase = 0;
     unsigned long long acc_et = 0, acc_er = 0, acc_ef = 0, n_items = 0;
-    cg::ChainPos pos; pos.g = pidx; pos.base = 0; pos.l = 0;
+    cg::ChainPos pos; pos.init(pidx);
     for (; pos.g < cp.total_items; pos.g += npairs) {
       pos.seek(cp);
       const ChainLayer& L = cp.L[pos.l];
@@ -417,10 +445,10 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
       uint32_t stored = 0;            // chunks stored so far == store groups committed
       uint32_t freed = 0;             // stores whose staging buffer has been handed back (store_free arrived)
       // walk of the chunks to store
-      cg::ChainPos pos; pos.g = pidx; pos.base = 0; pos.l = 0;
+      cg::ChainPos pos; pos.init(pidx);
       int sc = 0;                     // next chunk of item pos
       // walk of the residual chunks to fetch (runs ahead)
-      cg::ChainPos pf; pf.g = pidx; pf.base = 0; pf.l = 0;
+      cg::ChainPos pf; pf.init(pidx);
       uint32_t pf_ord = 0, pf_j = 0; int pf_c = 0;
       // completion signals: pushed here as (counter address, store-group sequence), fired by the signal thread (warp 7)
       // once this thread has seen that group written (cp.async.bulk.wait_group is per thread) and published `completed`
@@ -459,11 +487,14 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
       while (pos.g < cp.total_items) {
         if (!have_item) {
           pos.seek(cp);
-          if (pos.l != cur_l) {
-            const CUtensorMap* tm = cp.maps + 4 * pos.l + 2;
-            if (cur_l < 0) { cg::prefetch_tmap(tm); cg::prefetch_tmap(tm + 1); }
-            if (pos.l + 1 < cp.n_layers) { cg::prefetch_tmap(tm + 4); cg::prefetch_tmap(tm + 5); }
-            cur_l = pos.l;
+          if (pos.s != cur_l) {
+            if (cur_l < 0) { cg::prefetch_tmap(cp.maps + 4 * pos.l + 2); cg::prefetch_tmap(cp.maps + 4 * pos.l + 3); }
+            if (pos.s + 1 < cp.n_segs) {
+              const ChainSeg& NS = cp.S[pos.s + 1];
+              cg::prefetch_tmap(cp.maps + 4 * NS.lx + 2); cg::prefetch_tmap(cp.maps + 4 * NS.lx + 3);
+              if (NS.ly >= 0) { cg::prefetch_tmap(cp.maps + 4 * NS.ly + 2); cg::prefetch_tmap(cp.maps + 4 * NS.ly + 3); }
+            }
+            cur_l = pos.s;
           }
           pos.coords(cp, (int)crank, n0, x0, y0, img, mt);
           nchunks = cp.L[pos.l].bn >> 6;

@@ -233,6 +233,8 @@ int chain_plan_build(mrcnn_ctx* ctx, const std::vector<ConvLaunch>& layers, Chai
   uint32_t items = 0;
   double flops = 0;
   long max_tiles_m = 0;
+  std::vector<uint32_t> layer_pm(nl);
+  std::vector<long> layer_tiles_m(nl);
   const int n_img = layers[0].n;
   for (int l = 0; l < nl; ++l) {
     ConvLaunch L = layers[l];
@@ -253,8 +255,8 @@ int chain_plan_build(mrcnn_ctx* ctx, const std::vector<ConvLaunch>& layers, Chai
     MRCNN_REQUIRE(ctx, p.tiles_x * p.tiles_y <= 65535 && p.tiles_n <= 65535, "chain: too many tiles per image");
     ChainLayer& C = cp.L[l];
     const long tiles_m = (long)p.n_img * p.tiles_x * p.tiles_y;
-    items += (uint32_t)(((tiles_m + 1) / 2) * p.tiles_n);
-    C.item_end = items;
+    layer_pm[l] = (uint32_t)((tiles_m + 1) / 2);           // pair tiles (256 pixels) of this layer
+    layer_tiles_m[l] = tiles_m;
     C.tiles_x = (uint16_t)p.tiles_x; C.tiles_y = (uint16_t)p.tiles_y; C.tiles_n = (uint16_t)p.tiles_n;
     C.tiles_per_img = (uint16_t)(p.tiles_x * p.tiles_y);
     C.cout = (uint16_t)p.cout; C.bn = (uint16_t)cpl.bn; C.cin_chunks = (uint16_t)(p.cin / CG_BK);
@@ -291,6 +293,44 @@ int chain_plan_build(mrcnn_ctx* ctx, const std::vector<ConvLaunch>& layers, Chai
     writer[L.out] = l;
     maps[4 * l + 0] = cpl.tmA; maps[4 * l + 1] = cpl.tmB; maps[4 * l + 2] = cpl.tmC; maps[4 * l + 3] = cpl.tmR;
     flops += cpl.flops;
+  }
+  // ---- the work list.  Two halves of the batch run `lag` layers apart and are zipped (see ChainSeg): each half is
+  // dependency-closed (whole images), so every dependency still points backwards in the list.
+  {
+    const char* e = getenv("MRCNN_CHAIN_LAG");
+    int lag = e ? atoi(e) : 0;      // measured on B200: the lagged order stalls more than it overlaps; kept for experiments
+    const int img_a = n_img / 2;                                   // images of the first half
+    bool split = lag > 0 && n_img >= 2;
+    for (int l = 0; l < nl && split; ++l)
+      if (((long)cp.L[l].tiles_per_img * img_a) % 2 != 0) split = false;     // a CTA pair must not straddle the halves
+    int ns = 0;
+    auto push = [&](int lx, uint32_t x0, uint32_t nx, int ly, uint32_t y0, uint32_t ny) -> bool {
+      if (nx == 0 && ny == 0) return true;
+      if (ns >= CH_MAX_SEGS) return false;
+      ChainSeg& G = cp.S[ns++];
+      if (nx == 0) { lx = ly; x0 = y0; nx = ny; ly = -1; y0 = 0; ny = 0; }
+      if (ny == 0) ly = -1;
+      items += nx + ny;
+      G.item_end = items; G.lx = (int16_t)lx; G.ly = (int16_t)ly; G.x0 = x0; G.y0 = y0; G.nx = nx; G.ny = ny;
+      return true;
+    };
+    bool ok = true;
+    if (!split) {
+      for (int l = 0; l < nl && ok; ++l) ok = push(l, 0, layer_pm[l] * cp.L[l].tiles_n, -1, 0, 0);
+    } else {
+      for (int t = 0; t < nl + lag && ok; ++t) {
+        const int la = t < nl ? t : -1, lb = t - lag >= 0 ? t - lag : -1;
+        uint32_t xa0 = 0, na = 0, yb0 = 0, nb = 0;
+        if (la >= 0) { const uint32_t pa = (uint32_t)((long)cp.L[la].tiles_per_img * img_a / 2); na = pa * cp.L[la].tiles_n; xa0 = 0; }
+        if (lb >= 0) {
+          const uint32_t pa = (uint32_t)((long)cp.L[lb].tiles_per_img * img_a / 2);
+          yb0 = pa * cp.L[lb].tiles_n; nb = (layer_pm[lb] - pa) * cp.L[lb].tiles_n;
+        }
+        ok = push(la, xa0, na, lb, yb0, nb);
+      }
+    }
+    MRCNN_REQUIRE(ctx, ok, "chain: too many segments");
+    cp.n_segs = ns;
   }
   cp.n_layers = nl; cp.n_img = n_img; cp.total_items = items;
   cp.flag_stride = (int)((max_tiles_m + 15) / 16 * 16);

@@ -112,9 +112,9 @@ def fold(params, architecture=101, num_classes=81, pool_classifier=7):
             b = np.tile(b, kh * kw)
         else:
             w = np.transpose(k, (3, 0, 1, 2))               # HWIO -> OHWI
-        if has_bn:
-            gamma, beta, mean, var = [x.astype(np.float64) for x in p["bn"]]
-            scale = gamma / np.sqrt(var + BN_EPS)
+        if "bn" in p:                 # (imported artefacts may come with the batch norm already fused: no "bn" then)
+            gamma, beta, mean, var = [np.asarray(x).astype(np.float64) for x in p["bn"]]
+            scale = gamma / np.sqrt(var + float(p.get("bn_eps", BN_EPS)))
             w = w * scale[:, None, None, None]
             b = (b - mean) * scale + beta
         out[name] = (np.ascontiguousarray(w).astype(np.float16), b.astype(np.float32))

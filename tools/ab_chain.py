@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """A/B of the chained ResNet stages (conv_chain.cuh) against layer-by-layer launches in ONE process: two models, the
 predict calls of both interleaved, CUDA-event timed; prints the median / min milliseconds per batch of every variant.
-  VARIANTS="0:0 1:4 1:14 1:15"  (MRCNN_CHAIN:MRCNN_CHAIN_STAGES)"""
+  VARIANTS="0:0 1:4 1:14:0 1:15"  (MRCNN_CHAIN:MRCNN_CHAIN_STAGES[:MRCNN_CHAIN_LAG])"""
 import os
 import sys
 
@@ -23,9 +23,10 @@ def main():
     models = []
     stream = torch.cuda.Stream()
     for v in variants:
-        c, mask = v.split(":")
+        c, mask, *rest = v.split(":")
         os.environ["MRCNN_CHAIN"] = c
         os.environ["MRCNN_CHAIN_STAGES"] = mask
+        os.environ["MRCNN_CHAIN_LAG"] = rest[0] if rest else "2"
         for k in ("MRCNN_CHAIN_MAXLEN",):
             os.environ.pop(k, None)
         cfg = m.MaskRCNNConfig()
