@@ -60,8 +60,6 @@ struct ConvGemmParams {
   int ctas;                    // 1 or 2 (CTA pair / cta_group::2), must match the kernel instantiation and the cluster launch
   int nstages;                 // depth of the operand ring (A+B tiles), chosen per layer by the host
   int nbuf_log2;               // log2 of the number of 16 KB output / residual staging buffers (1 or 2)
-  int tail_full_wait;          // 1: the last TMA store of a CTA is waited for until its global writes completed (default: only until
-                               //    its smem reads completed -- grid completion makes the writes visible to the next kernel)
   int split_out;               // 1: outputs written as fp16 (hi, lo) pairs: channels [0,cout) = hi, [cout,2cout) = lo (2-term activations)
   int md_precise;              // maskdot: keep the activation in fp32 (no fp16 rounding before the class dot product)
   int maskdot;                 // 1: mask-head tail fused into the deconv epilogue (see epilogue_maskdot)
@@ -417,7 +415,7 @@ __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, const C
     }
     if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
   }
-  if (e0) { if (p.tail_full_wait) bulk_wait<0>(); else bulk_wait_read<0>(); }
+  if (e0) bulk_wait<0>();
 }
 
 // ---- 2-term ("split") outputs for the precise mask head: every activation v is stored as hi = fp16(v) and

@@ -173,11 +173,6 @@ int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan) {
   p.tma_out = (!L.no_tma_epilogue && !L.out_f32 && !L.deconv && (L.cout % 64) == 0 && bn >= 64) ? 1 : 0;
   p.tma_res = (p.tma_out && p.res_mode == 1) ? 1 : 0;
   p.trace = L.trace;
-  {
-    static int env_tail = -1;
-    if (env_tail < 0) { const char* e = getenv("MRCNN_CONV_TAIL_FULL_WAIT"); env_tail = e ? atoi(e) : 0; }
-    p.tail_full_wait = env_tail;
-  }
   p.split_out = L.split_out;
   p.md_precise = L.md_precise;
   if (L.split_out) {

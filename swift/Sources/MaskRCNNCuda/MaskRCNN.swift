@@ -82,6 +82,23 @@ public final class MaskRCNN {
         return (det, msk)
     }
 
+    /// Streaming: the loop of EvaluateCommand.swift:166-194 with two batches in flight.  `submit` enqueues a batch and
+    /// returns at once (the host->device copy of this batch overlaps the compute of the previous one); `wait` blocks
+    /// until the OLDEST submitted batch is complete.  The buffers (ideally page-locked) must stay valid and untouched
+    /// until the matching `wait` returns.  At most two batches may be in flight.
+    public func submit(images: UnsafePointer<UInt8>, batch: Int, detections: UnsafeMutablePointer<Float>,
+                       masks: UnsafeMutablePointer<Float>) throws {
+        let status = mrcnn_predict_submit(ctx, Int32(batch), images, detections, masks, 0)
+        if status != 0 { throw MaskRCNNError(status: status, description: String(cString: mrcnn_last_error(ctx))) }
+    }
+
+    public func wait() throws {
+        let status = mrcnn_predict_wait(ctx)
+        if status != 0 { throw MaskRCNNError(status: status, description: String(cString: mrcnn_last_error(ctx))) }
+    }
+
+    public var batchesInFlight: Int { return Int(mrcnn_predict_in_flight(ctx)) }
+
     /// One image -> [Detection] with score > 0.7, as ViewController.swift:163-187 does with the Core ML outputs.
     public func predict(image: UnsafePointer<UInt8>) throws -> [Detection] {
         let out = try prediction(images: image, batch: 1)

@@ -264,10 +264,11 @@ def _model_with_env(pkg, monkeypatch, chain, arch=50, size=SIZE, batch=2, pre=10
     return pkg.MaskRCNN(cfg, blobs=blobs, anchors=pkg.synth.generate_anchors(size, size))
 
 
-@pytest.mark.parametrize("batch", [1, 2, 3])
-def test_chained_stages_bit_identical_to_layerwise_launches(pkg, small, monkeypatch, batch):
+@pytest.mark.parametrize("batch,lag", [(1, 0), (2, 0), (3, 0), (2, 2), (3, 1)])
+def test_chained_stages_bit_identical_to_layerwise_launches(pkg, small, monkeypatch, batch, lag):
     """The persistent per-stage chain kernel (conv_chain.cuh: all layers of a ResNet stage in one launch, image-granular
     dataflow between layers) must reproduce the layer-by-layer launches bit for bit: feature maps, RPN outputs."""
+    monkeypatch.setenv("MRCNN_CHAIN_LAG", str(lag))          # > 0: two halves of the batch `lag` layers apart, zipped segments
     rng = np.random.default_rng(batch)
     img = rng.integers(0, 256, (batch, SIZE, SIZE, 3), dtype=np.uint8)
     outs = []
