@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmaskrcnn_cuda.so")
+# MRCNN_LIB_PATH: another build of the same library (A/B measurements of kernel changes on one box)
+LIB_PATH = os.environ.get("MRCNN_LIB_PATH") or os.path.join(_HERE, "libmaskrcnn_cuda.so")
 
 OK, EINVAL, ECUDA, ENCCL, EIO, ESTATE = 0, -1, -2, -3, -4, -5
 

@@ -314,14 +314,20 @@ __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, const C
   int acc = 0; uint32_t acc_phase = 0;
   // residual prefetch (RES == 1): chunk j of this CTA = work item first + (j / nchunks) * step, chunk j % nchunks
   const uint32_t my_chunks = (uint32_t)(ts.count() * nchunks);
+  // (the tile coordinates of the chunk being fetched are cached: they change once per nchunks calls, and this runs on
+  // the one thread the other 127 epilogue threads wait for at the next barrier)
+  uint32_t lr_tile = 0xffffffffu;
+  int lr_n0 = 0, lr_x0 = 0, lr_y0 = 0, lr_img = 0;
   auto load_residual = [&](uint32_t j) {
     if (j >= my_chunks) return;
-    const int t = ts.first + (int)(j / (uint32_t)nchunks) * ts.step;
-    int n0, x0, y0, img;
-    ts.coords(p, BN, t, n0, x0, y0, img);
+    const uint32_t ti = j / (uint32_t)nchunks;
+    if (ti != lr_tile) {
+      lr_tile = ti;
+      ts.coords(p, BN, ts.first + (int)ti * ts.step, lr_n0, lr_x0, lr_y0, lr_img);
+    }
     const uint32_t b = j & nb_mask;
     mbar_expect_tx(rfull0 + 8u * b, (uint32_t)kStageBytes);
-    tma_load_4d(out_base + b * (uint32_t)kStageBytes, tmR, rfull0 + 8u * b, n0 + (int)(j % (uint32_t)nchunks) * 64, x0, y0, img);
+    tma_load_4d(out_base + b * (uint32_t)kStageBytes, tmR, rfull0 + 8u * b, lr_n0 + (int)(j - ti * (uint32_t)nchunks) * 64, lr_x0, lr_y0, lr_img);
   };
   TraceCursor tc = trace_open(p, 2);
   if (!e0) tc.base = nullptr;

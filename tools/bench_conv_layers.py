@@ -75,6 +75,8 @@ def main():
         wt = torch.randn((cout, k, k, cin), device="cuda", dtype=torch.float16) * 0.05
         bias = torch.zeros(cout, device="cuda")
         out = torch.empty((n, ho, wo, ldc), device="cuda", dtype=torch.float16)
+        # the last 1x1 of every bottleneck adds the block input (TMA-fetched residual epilogue)
+        res = torch.randn((n, ho, wo, ldc), device="cuda", dtype=torch.float16) if tag.endswith(" 2c") else None
         ts = []
         with torch.cuda.stream(st):
             for r in range(args.reps + 2):
@@ -82,7 +84,7 @@ def main():
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 rc = lib.mrcnn_conv2d_nhwc_f16(ctx.handle, x.data_ptr(), n, h, w, cin, wt.data_ptr(), bias.data_ptr(), cout, k, k, stride,
-                                               pad, None, 1, out.data_ptr())
+                                               pad, res.data_ptr() if res is not None else None, 1, out.data_ptr())
                 e1.record()
                 m._cabi.check(ctx.handle, rc)
                 st.synchronize()
@@ -90,9 +92,9 @@ def main():
                     ts.append(e0.elapsed_time(e1))
         ms = float(np.median(ts))
         flops = 2.0 * n * ho * wo * cout * k * k * cin
-        byts = 2.0 * (x.numel() + out.numel() + wt.numel())
+        byts = 2.0 * (x.numel() + out.numel() + wt.numel() + (res.numel() if res is not None else 0))
         rows.append((tag, n, h, w, cin, cout, k, stride, count, ms, flops, byts))
-        del x, wt, out
+        del x, wt, out, res
     total = sum(r[8] * r[9] for r in rows)
     print(f"{'layer':20s} {'n':>5s} {'hxw':>11s} {'cin':>6s} {'cout':>5s} k s  cnt    ms/launch  TFLOP/s   GB/s  ms/step share")
     for tag, n, h, w, cin, cout, k, stride, count, ms, flops, byts in sorted(rows, key=lambda r: -r[8] * r[9]):
