@@ -49,9 +49,10 @@ struct DenseModel {
   int n_ev = 0;
   const char* ev_name[16] = {nullptr};
   // ---- streaming prediction (mrcnn_predict_submit / mrcnn_predict_wait): two batches in flight ----
-  struct StreamSlot { cudaEvent_t h2d_done = nullptr, done = nullptr; };
+  struct StreamSlot { cudaEvent_t h2d_done = nullptr, computed = nullptr, done = nullptr; };
   StreamSlot slot[2];
   cudaStream_t copy_stream = nullptr;   // H2D of batch i+1 runs here while batch i computes on ctx->stream
+  cudaStream_t copy_out_stream = nullptr;   // D2H of batch i runs here while batch i+1 computes
   uint64_t submitted = 0, completed = 0;
 };
 
@@ -118,9 +119,11 @@ void dense_destroy(mrcnn_ctx* ctx) {
   for (int i = 0; i < 16; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
   for (int i = 0; i < 2; ++i) {
     if (m->slot[i].h2d_done) cudaEventDestroy(m->slot[i].h2d_done);
+    if (m->slot[i].computed) cudaEventDestroy(m->slot[i].computed);
     if (m->slot[i].done) cudaEventDestroy(m->slot[i].done);
   }
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  if (m->copy_out_stream) cudaStreamDestroy(m->copy_out_stream);
   delete m;
   ctx->dense = nullptr;
 }
@@ -916,8 +919,10 @@ MRCNN_API int mrcnn_predict_submit(mrcnn_ctx* ctx, int batch, const uint8_t* rgb
   const int k = (int)(m->submitted & 1);
   DenseModel::StreamSlot& sl = m->slot[k];
   if (!m->copy_stream) MRCNN_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  if (!m->copy_out_stream) MRCNN_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&m->copy_out_stream, cudaStreamNonBlocking));
   if (!sl.done) {
     MRCNN_CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+    MRCNN_CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl.computed, cudaEventDisableTiming));
     MRCNN_CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
   }
   // Per-slot device mirrors of host arguments.  A slot is only reused after the batch that used it was waited for
@@ -950,9 +955,16 @@ MRCNN_API int mrcnn_predict_submit(mrcnn_ctx* ctx, int batch, const uint8_t* rgb
   float* dmask = mask_host ? (float*)m->bufs[nm_mask[k]].p : masks;
   if (gather) TRY(predict_allgather_device(ctx, batch, drgb, ddet, dmask));
   else TRY(predict_device(ctx, batch, drgb, ddet, dmask));
-  if (det_host) MRCNN_CUDA_TRY(ctx, cudaMemcpyAsync(detections, ddet, det_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  if (mask_host) MRCNN_CUDA_TRY(ctx, cudaMemcpyAsync(masks, dmask, mask_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  MRCNN_CUDA_TRY(ctx, cudaEventRecord(sl.done, ctx->stream));
+  if (det_host || mask_host) {
+    // results leave on their own stream, under the compute of the next batch (which writes the other slot's mirrors)
+    MRCNN_CUDA_TRY(ctx, cudaEventRecord(sl.computed, ctx->stream));
+    MRCNN_CUDA_TRY(ctx, cudaStreamWaitEvent(m->copy_out_stream, sl.computed, 0));
+    if (det_host) MRCNN_CUDA_TRY(ctx, cudaMemcpyAsync(detections, ddet, det_bytes, cudaMemcpyDeviceToHost, m->copy_out_stream));
+    if (mask_host) MRCNN_CUDA_TRY(ctx, cudaMemcpyAsync(masks, dmask, mask_bytes, cudaMemcpyDeviceToHost, m->copy_out_stream));
+    MRCNN_CUDA_TRY(ctx, cudaEventRecord(sl.done, m->copy_out_stream));
+  } else {
+    MRCNN_CUDA_TRY(ctx, cudaEventRecord(sl.done, ctx->stream));
+  }
   m->submitted++;
   return MRCNN_OK;
 }
