@@ -254,8 +254,8 @@ MRCNN_API int mrcnn_predict_allgather(mrcnn_ctx* ctx, int batch_local, const uin
                             float* detections_all, float* masks_all);
 
 /* ---- Streaming prediction: the same pipeline with two batches in flight, so that the host->device copy of batch
- * i+1 (own copy stream) overlaps the compute of batch i and the caller prepares the next batch while the GPU
- * works.  The reference predicts image after image from a loop (EvaluateCommand.swift:166-194); this is that loop
+ * i+1 and the device->host copy of batch i-1 (own copy streams) overlap the compute of batch i and the caller
+ * prepares the next batch while the GPU works.  The reference predicts image after image from a loop (EvaluateCommand.swift:166-194); this is that loop
  * with the copies taken off the critical path.
  *   mrcnn_predict_submit  enqueues one batch and returns without waiting.  Arguments as mrcnn_predict (or, with
  *                         MRCNN_SUBMIT_ALLGATHER, as mrcnn_predict_allgather).  Host buffers should be pinned and
