@@ -73,6 +73,14 @@ struct ConvGemmParams {
   void* out;
   int8_t tap_dx[CG_MAX_TAPS];  // input offset of each tap, padding already subtracted
   int8_t tap_dy[CG_MAX_TAPS];
+  // vertical tap groups (vgroup > 1): taps t*vgroup .. t*vgroup + vgroup-1 have the same dx and dy = dy0, dy0+1, ...; their A
+  // tiles are `vgroup` overlapping windows of ONE (th + vgroup - 1)-row patch, loaded once (tmA's box has that height) and
+  // addressed by the MMA at row offsets dy * tw: 3x3 convolutions load 3 patches of 10 rows instead of 9 tiles of 8 rows
+  // per 64 input channels (2.4x less L2 -> SM traffic for A), the stem 1 patch of 11 rows instead of 4 tiles.
+  int vgroup;                  // 1: one A tile per tap (the layout above)
+  int na_stages;               // depth of the patch ring (vgroup > 1; the ring of `nstages` slots then holds B tiles only)
+  int patch_bytes;             // bytes of one patch slot (multiple of 1024)
+  int8_t tap_widx[CG_MAX_TAPS];   // vgroup > 1: position of tap t in the weight matrix's K order
 };
 
 namespace cg {
@@ -598,17 +606,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // 1024-B aligned operand ring (SWIZZLE_128B requirement)
   const uint32_t smem_base = (cg::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int nst = p.nstages;
-  const uint32_t ring_bytes = (uint32_t)nst * (uint32_t)C::kStageBytes;
+  const bool vg = p.vgroup > 1;
+  const int nsa = vg ? p.na_stages : 0;
+  // vgroup > 1: [patch ring: na_stages x patch_bytes][B ring: nstages x kBBytes]; else [nstages x (A tile + B tile)]
+  const uint32_t b_ring = smem_base + (uint32_t)nsa * (uint32_t)p.patch_bytes;
+  const uint32_t ring_bytes = vg ? (uint32_t)nsa * (uint32_t)p.patch_bytes + (uint32_t)nst * (uint32_t)C::kBBytes
+                                 : (uint32_t)nst * (uint32_t)C::kStageBytes;
   const uint32_t out_bytes = (uint32_t)C::kOutStageBytes << p.nbuf_log2;
   const uint32_t out_base = smem_base + ring_bytes;                      // nbuf x 16 KB output / residual staging
   const uint32_t bar_base = out_base + out_bytes;
-  // barriers (fixed layout): full[8] @0, empty[8] @64, tmem_full[2] @128, tmem_empty[2] @144, TMEM base slot @160, res_full[4] @168
+  // barriers (fixed layout): full[8] @0, empty[8] @64, tmem_full[2] @128, tmem_empty[2] @144, TMEM base slot @160, res_full[4] @168,
+  // patch_full[3] @200, patch_empty[3] @224
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
   auto tfull_bar = [&](int a) { return bar_base + 128u + 8u * a; };
   auto tempty_bar = [&](int a) { return bar_base + 144u + 8u * a; };
   const uint32_t tmem_slot = bar_base + 160u;
   auto rfull_bar = [&](int b) { return bar_base + 168u + 8u * b; };
+  auto afull_bar = [&](int s) { return bar_base + 200u + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar_base + 224u + 8u * s; };
   uint8_t* smem_gen = smem_raw + (smem_base - cg::smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + ring_bytes + out_bytes + 160u);
 
@@ -624,6 +640,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < nst; ++s) { cg::mbar_init(full_bar(s), 1); cg::mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { cg::mbar_init(tfull_bar(a), 1); cg::mbar_init(tempty_bar(a), 4 * CTAS); }
     for (int b = 0; b < 4; ++b) cg::mbar_init(rfull_bar(b), 1);
+    for (int a = 0; a < 3; ++a) { cg::mbar_init(afull_bar(a), 1); cg::mbar_init(aempty_bar(a), 1); }
     cg::fence_barrier_init();
   }
   if (warp == 1) { if (CTAS == 2) cg::tmem_alloc_2cta(tmem_slot, C::kTmemCols); else cg::tmem_alloc(tmem_slot, C::kTmemCols); }
@@ -649,7 +666,47 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA stages its own A rows and its share of B) =====================
-    if (lane == 0) {
+    if (lane == 0 && vg) {
+      // patch ring + B ring (see ConvGemmParams::vgroup)
+      int sb = 0; uint32_t phb = 0;
+      int sa = 0; uint32_t pha = 0;
+      const int V = p.vgroup, ngroups = p.ntaps / V;
+      const uint32_t a_tx = (uint32_t)p.tw * (uint32_t)(p.th + V - 1) * 128u * (uint32_t)CTAS;
+      for (int w = ts.first; w < ts.total; w += ts.step) {
+        int n0, px0, py0, img;
+        ts.coords(p, BN, w, n0, px0, py0, img);
+        const int x0 = px0 * p.stride, y0 = py0 * p.stride;
+        const int nb0 = n0 + (int)crank * (BN / CTAS);
+        for (int g = 0; g < ngroups; ++g) {
+          const int xi = x0 + p.tap_dx[g * V], yi = y0 + p.tap_dy[g * V];
+          for (int cc = 0; cc < cin_chunks; ++cc) {
+            cg::mbar_wait(aempty_bar(sa), pha ^ 1u);
+            const uint32_t a_dst = smem_base + (uint32_t)sa * (uint32_t)p.patch_bytes;
+            if (CTAS == 2) {
+              if (crank == 0) cg::mbar_expect_tx(afull_bar(sa), a_tx);
+              cg::tma_load_4d_2cta(a_dst, &tmA, cg::mapa_rank(afull_bar(sa), 0), cc * CG_BK, xi, yi, img);
+            } else {
+              cg::mbar_expect_tx(afull_bar(sa), a_tx);
+              cg::tma_load_4d(a_dst, &tmA, afull_bar(sa), cc * CG_BK, xi, yi, img);
+            }
+            if (++sa == nsa) { sa = 0; pha ^= 1u; }
+            for (int v = 0; v < V; ++v) {
+              cg::mbar_wait(empty_bar(sb), phb ^ 1u);
+              const uint32_t b_dst = b_ring + (uint32_t)sb * (uint32_t)C::kBBytes;
+              const int kcol = (int)p.tap_widx[g * V + v] * p.cin + cc * CG_BK;
+              if (CTAS == 2) {
+                if (crank == 0) cg::mbar_expect_tx(full_bar(sb), (uint32_t)(2 * C::kBBytes));
+                cg::tma_load_2d_2cta(b_dst, &tmB, cg::mapa_rank(full_bar(sb), 0), kcol, nb0);
+              } else {
+                cg::mbar_expect_tx(full_bar(sb), (uint32_t)C::kBBytes);
+                cg::tma_load_2d(b_dst, &tmB, full_bar(sb), kcol, nb0);
+              }
+              if (++sb == nst) { sb = 0; phb ^= 1u; }
+            }
+          }
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       cg::TraceCursor tc = cg::trace_open(p, 0);
       for (int w = ts.first; w < ts.total; w += ts.step) {
@@ -681,7 +738,42 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread; of the leader CTA in a pair) =====================
-    if (lane == 0 && crank == 0) {
+    if (lane == 0 && crank == 0 && vg) {
+      constexpr uint32_t idesc = cg::make_idesc_f16(CG_BM * CTAS, BN);
+      int sb = 0; uint32_t phb = 0;
+      int sa = 0; uint32_t pha = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      const int V = p.vgroup, npatch = (p.ntaps / V) * cin_chunks;
+      const uint32_t row_step = (uint32_t)p.tw * 128u;          // one tile row further down in the patch (a multiple of 1024 B)
+      for (int w = ts.first; w < ts.total; w += ts.step) {
+        cg::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        cg::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        uint32_t first = 0u;
+        for (int pi = 0; pi < npatch; ++pi) {
+          cg::mbar_wait(afull_bar(sa), pha);
+          const uint32_t a_addr = smem_base + (uint32_t)sa * (uint32_t)p.patch_bytes;
+          for (int v = 0; v < V; ++v) {
+            cg::mbar_wait(full_bar(sb), phb);
+            cg::tc_fence_after();
+            const uint64_t adesc = cg::make_sw128_desc(a_addr + (uint32_t)v * row_step);
+            const uint64_t bdesc = cg::make_sw128_desc(b_ring + (uint32_t)sb * (uint32_t)C::kBBytes);
+            #pragma unroll
+            for (int k = 0; k < CG_BK / 16; ++k) {
+              if (CTAS == 2) cg::umma_f16_2cta(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
+              else cg::umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
+            }
+            first = 1u;
+            if (CTAS == 2) cg::umma_commit_2cta(empty_bar(sb)); else cg::umma_commit(empty_bar(sb));      // B slot free when these MMAs retire
+            if (++sb == nst) { sb = 0; phb ^= 1u; }
+          }
+          if (CTAS == 2) cg::umma_commit_2cta(aempty_bar(sa)); else cg::umma_commit(aempty_bar(sa));      // patch free after its last window
+          if (++sa == nsa) { sa = 0; pha ^= 1u; }
+        }
+        if (CTAS == 2) cg::umma_commit_2cta(tfull_bar(acc)); else cg::umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    } else if (lane == 0 && crank == 0) {
       constexpr uint32_t idesc = cg::make_idesc_f16(CG_BM * CTAS, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;

@@ -135,6 +135,55 @@ int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan) {
   plan->grid = (int)((total_items < slots ? total_items : slots) * ctas);
   plan->flops = 2.0 * p.n_img * p.h_out * p.w_out * (double)L.cout * ntaps * L.cin;
 
+  // ---- epilogue kind and shared-memory split
+  p.split_out = L.split_out;
+  p.tma_out = (!L.split_out && !L.no_tma_epilogue && !L.out_f32 && !L.deconv && (L.cout % 64) == 0 && bn >= 64) ? 1 : 0;
+  p.tma_res = (p.tma_out && p.res_mode == 1) ? 1 : 0;
+  // ring depth vs staging depth (see cg::Cfg): memory-bound layers (few K blocks per tile, or a TMA-fetched residual)
+  // trade ring stages for staging buffers so that the residual is prefetched further ahead and more stores are in flight
+  {
+    const int nkb = ntaps * (L.cin / CG_BK);
+    const bool deep_staging = (p.tma_out && (p.tma_res || nkb <= 4)) || L.split_out;   // split outputs use 4 staging buffers
+    const int deep[2][4] = {{8, 8, 6, 4}, {8, 8, 8, 6}}, shrt[2][4] = {{6, 6, 5, 3}, {8, 8, 6, 5}};     // [ctas-1][BN = 32, 64, 128, 256]
+    const int bi = bn == 32 ? 0 : (bn == 64 ? 1 : (bn == 128 ? 2 : 3));
+    p.nstages = deep_staging ? shrt[ctas - 1][bi] : deep[ctas - 1][bi];
+    p.nbuf_log2 = deep_staging ? 2 : 1;
+  }
+  // Vertical tap groups (ConvGemmParams::vgroup): consecutive taps that differ only by dy = 0, 1, 2, ... share one A patch.
+  // 3x3 stride-1 convolutions: taps reordered (dx, dy) -> 3 groups of 3; the stem's 4 vertical taps are one group already.
+  // The patch ring (3 slots) + the B ring live in the shared-memory budget of the (A + B) ring they replace.
+  p.vgroup = 1; p.na_stages = 0; p.patch_bytes = 0;
+  for (int t = 0; t < ntaps; ++t) p.tap_widx[t] = (int8_t)t;
+  {
+    const char* e = getenv("MRCNN_CONV_VGROUP");          // 0: one A tile per tap everywhere (A/B measurements, tests)
+    const int env_vg = e ? atoi(e) : 1;
+    int vgr = 1;
+    if (env_vg && !L.no_vgroup && L.stride == 1 && !L.deconv && !L.trace) {
+      if (!L.ntaps_override && L.kh == 3 && L.kw == 3) vgr = 3;
+      else if (L.ntaps_override >= 2 && L.ntaps_override <= 4) {
+        bool vertical = true;
+        for (int t = 0; t < ntaps; ++t) vertical = vertical && p.tap_dx[t] == p.tap_dx[0] && p.tap_dy[t] == p.tap_dy[0] + t;
+        if (vertical) vgr = ntaps;
+      }
+    }
+    if (vgr > 1) {
+      const int a_bytes = CG_BM * CG_BK * 2, b_bytes = (bn / ctas) * CG_BK * 2;
+      const int budget = p.nstages * (a_bytes + b_bytes);
+      const int patch = (p.tw * (p.th + vgr - 1) * 128 + 1023) / 1024 * 1024;
+      int nb = (budget - 3 * patch) / b_bytes;
+      if (nb > 8) nb = 8;
+      if (nb >= 3 && (p.th + vgr - 1) <= 256) {
+        p.vgroup = vgr; p.na_stages = 3; p.patch_bytes = patch; p.nstages = nb;
+        if (vgr == 3 && !L.ntaps_override)
+          for (int kx = 0; kx < 3; ++kx)
+            for (int ky = 0; ky < 3; ++ky) {
+              p.tap_dx[kx * 3 + ky] = (int8_t)(kx - L.pad); p.tap_dy[kx * 3 + ky] = (int8_t)(ky - L.pad);
+              p.tap_widx[kx * 3 + ky] = (int8_t)(ky * 3 + kx);
+            }
+      }
+    }
+  }
+
   // ---- A: 4-D (C, W, H, N) view of the NHWC activation, box (64, tw*s, th*s, 1), traversal stride s
   cuuint64_t adims[4], astr[3];
   if (L.custom_view) {
@@ -144,7 +193,7 @@ int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan) {
     adims[0] = (cuuint64_t)L.cin; adims[1] = (cuuint64_t)L.w_in; adims[2] = (cuuint64_t)L.h_in; adims[3] = (cuuint64_t)L.n;
     astr[0] = (cuuint64_t)ld_in * 2; astr[1] = astr[0] * L.w_in; astr[2] = astr[1] * L.h_in;
   }
-  cuuint32_t abox[4] = {(cuuint32_t)CG_BK, (cuuint32_t)(p.tw * L.stride), (cuuint32_t)(p.th * L.stride), 1};
+  cuuint32_t abox[4] = {(cuuint32_t)CG_BK, (cuuint32_t)(p.tw * L.stride), (cuuint32_t)((p.th + p.vgroup - 1) * L.stride), 1};
   cuuint32_t aes[4] = {1, (cuuint32_t)L.stride, (cuuint32_t)L.stride, 1};
   CUresult r = enc(&plan->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)L.x, adims, astr, abox, aes,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -170,31 +219,17 @@ int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan) {
   }
   // ---- C (and residual R): 4-D (C, W, H, N) views of the NHWC fp16 output, box (64, tw, th, 1)
   plan->tmC = plan->tmB; plan->tmR = plan->tmB;      // valid placeholders when the staged epilogue is off
-  p.tma_out = (!L.no_tma_epilogue && !L.out_f32 && !L.deconv && (L.cout % 64) == 0 && bn >= 64) ? 1 : 0;
-  p.tma_res = (p.tma_out && p.res_mode == 1) ? 1 : 0;
   p.trace = L.trace;
-  p.split_out = L.split_out;
   p.md_precise = L.md_precise;
   if (L.split_out) {
     MRCNN_REQUIRE(ctx, !L.out_f32 && !L.deconv && !L.residual && (L.cout % 64) == 0 && bn >= 64 && p.ldc == 2 * L.cout,
                   "conv: split (hi, lo) outputs need an fp16 NHWC output of 2*cout channels, cout % 64 == 0, no residual");
-    p.tma_out = 0; p.tma_res = 0;
   }
   p.maskdot = L.maskdot;
   if (L.maskdot) {
     MRCNN_REQUIRE(ctx, L.deconv && L.deconv_c == 256 && bn == 256 && L.bias && L.md_valid && L.md_cls && L.md_w && L.md_b && L.md_ncls > 0,
                   "conv: the fused mask tail needs a 256-channel deconvolution with bias and the slot / class-weight arrays");
     p.md_valid = L.md_valid; p.md_cls = L.md_cls; p.md_w = L.md_w; p.md_b = L.md_b; p.md_ncls = L.md_ncls;
-  }
-  // ring depth vs staging depth (see cg::Cfg): memory-bound layers (few K blocks per tile, or a TMA-fetched residual)
-  // trade ring stages for staging buffers so that the residual is prefetched further ahead and more stores are in flight
-  {
-    const int nkb = ntaps * (L.cin / CG_BK);
-    const bool deep_staging = (p.tma_out && (p.tma_res || nkb <= 4)) || p.split_out;   // split outputs use 4 staging buffers
-    const int deep[2][4] = {{8, 8, 6, 4}, {8, 8, 8, 6}}, shrt[2][4] = {{6, 6, 5, 3}, {8, 8, 6, 5}};     // [ctas-1][BN = 32, 64, 128, 256]
-    const int bi = bn == 32 ? 0 : (bn == 64 ? 1 : (bn == 128 ? 2 : 3));
-    p.nstages = deep_staging ? shrt[ctas - 1][bi] : deep[ctas - 1][bi];
-    p.nbuf_log2 = deep_staging ? 2 : 1;
   }
   if (p.tma_out || p.split_out) {
     cuuint64_t cdims[4] = {(cuuint64_t)(p.split_out ? 2 * L.cout : L.cout), (cuuint64_t)p.w_out, (cuuint64_t)p.h_out, (cuuint64_t)L.n};
@@ -237,6 +272,7 @@ int chain_plan_build(mrcnn_ctx* ctx, const std::vector<ConvLaunch>& layers, Chai
     MRCNN_REQUIRE(ctx, L.cout % 64 == 0, "chain: cout must be a multiple of 64");
     MRCNN_REQUIRE(ctx, L.bias != nullptr, "chain: layers need a bias vector");
     L.ctas = 2;
+    L.no_vgroup = 1;
     L.bn = L.cout >= 256 ? 256 : L.cout;   // 64, 128 or 256: always divides cout here
     MRCNN_REQUIRE(ctx, L.cout % L.bn == 0, "chain: cout must be a multiple of the N tile");
     ConvPlan cpl;

@@ -32,6 +32,7 @@ struct ConvLaunch {
   unsigned long long* trace = nullptr;   // debug event trace buffer (device), see cg::trace_ev
   int ctas = 0;                  // 0 -> auto (env MRCNN_CONV_CTAS overrides), 1 = one CTA per tile, 2 = CTA pairs (cta_group::2)
   int no_tma_epilogue = 0;       // force the direct-store epilogue (tests)
+  int no_vgroup = 0;             // one A tile per tap even for 3x3 convolutions (the chain kernel has no patch ring)
   // mask-head tail fused into the deconv epilogue (needs deconv = 1, deconv_c == bn == 256): out = f32 [n, 2h, 2w]
   int maskdot = 0;
   const int32_t* md_valid = nullptr;

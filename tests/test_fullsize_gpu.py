@@ -83,6 +83,7 @@ def test_config_s_resnet50_512_predict_equals_stagewise_chain(pkg, orc, monkeypa
     img = rng.integers(0, 256, (2, size // 8, size // 8, 3)).astype(np.uint8).repeat(8, 1).repeat(8, 2)
     img = (img.astype(np.int32) + rng.integers(-20, 20, img.shape)).clip(0, 255).astype(np.uint8)
     results = []
+    monkeypatch.setenv("MRCNN_CONV_VGROUP", "0")      # the chained stages load one A tile per tap: same K order on both sides
     for chain in ("0", "1"):
         monkeypatch.setenv("MRCNN_CHAIN", chain)
         cfg = pkg.MaskRCNNConfig()
@@ -122,15 +123,18 @@ def test_config_s_resnet50_512_predict_equals_stagewise_chain(pkg, orc, monkeypa
 def test_fullsize_chained_stages_bit_identical(pkg, full, monkeypatch):
     """ResNet101 at 1024x1024: the chained stages (one persistent launch per ResNet stage) give the same detections and
     masks as the layer-by-layer launches."""
-    monkeypatch.setenv("MRCNN_CHAIN", "1")
-    cfg = pkg.MaskRCNNConfig()
-    cfg.maxBatch = 2
+    monkeypatch.setenv("MRCNN_CONV_VGROUP", "0")
     _, blobs = pkg.weights.synthetic_blobs(101)
-    m = pkg.MaskRCNN(cfg, blobs=blobs, anchors=full["anchors"])
-    try:
-        det, masks = m.prediction_batch(full["img"])
-    finally:
-        m.close()
-    want_det, want_masks = full["model"].prediction_batch(full["img"])
+    outs = []
+    for chain in ("1", "0"):
+        monkeypatch.setenv("MRCNN_CHAIN", chain)
+        cfg = pkg.MaskRCNNConfig()
+        cfg.maxBatch = 2
+        m = pkg.MaskRCNN(cfg, blobs=blobs, anchors=full["anchors"])
+        try:
+            outs.append(m.prediction_batch(full["img"]))
+        finally:
+            m.close()
+    (det, masks), (want_det, want_masks) = outs
     np.testing.assert_array_equal(det, want_det)
     np.testing.assert_array_equal(masks, want_masks)

@@ -269,6 +269,7 @@ def test_chained_stages_bit_identical_to_layerwise_launches(pkg, small, monkeypa
     """The persistent per-stage chain kernel (conv_chain.cuh: all layers of a ResNet stage in one launch, image-granular
     dataflow between layers) must reproduce the layer-by-layer launches bit for bit: feature maps, RPN outputs."""
     monkeypatch.setenv("MRCNN_CHAIN_LAG", str(lag))          # > 0: two halves of the batch `lag` layers apart, zipped segments
+    monkeypatch.setenv("MRCNN_CONV_VGROUP", "0")             # same K order on both sides (the chain kernel loads one A tile per tap)
     rng = np.random.default_rng(batch)
     img = rng.integers(0, 256, (batch, SIZE, SIZE, 3), dtype=np.uint8)
     outs = []
@@ -284,3 +285,24 @@ def test_chained_stages_bit_identical_to_layerwise_launches(pkg, small, monkeypa
         np.testing.assert_array_equal(outs[0][0][l], outs[1][0][l])
     np.testing.assert_array_equal(outs[0][1], outs[1][1])
     np.testing.assert_array_equal(outs[0][2], outs[1][2])
+
+
+def test_vertical_tap_groups_same_result_up_to_summation_order(pkg, small, monkeypatch):
+    """3x3 convolutions and the stem load one (th + 2)-row patch per horizontal tap offset and run the three vertical taps
+    as windows of it (ConvGemmParams::vgroup); that reorders the K loop, so against one-tile-per-tap launches the
+    results agree to fp32-accumulation-order noise, not bit for bit."""
+    outs = []
+    for v in ("0", "1"):
+        monkeypatch.setenv("MRCNN_CONV_VGROUP", v)
+        monkeypatch.setenv("MRCNN_CHAIN", "0")
+        model = _model_with_env(pkg, monkeypatch, False, batch=2)
+        try:
+            outs.append(_backbone(pkg, model, small["img"]))
+        finally:
+            model.close()
+    for l in range(4):
+        mx, mean = _relerr(outs[1][0][l].astype(np.float32), outs[0][0][l].astype(np.float32))
+        # different but close: every layer rounds its outputs to fp16, so a reordered fp32 sum flips roundings that then
+        # propagate through ~50 layers; measured 1.1e-3 (max) / 7e-4 (mean), the size of the fp16-vs-fp32 differences
+        assert 0 < mx < 4e-3 and mean < 2e-3, (l, mx, mean)
+    assert np.abs(outs[1][1] - outs[0][1]).max() < 2e-3
