@@ -1,5 +1,6 @@
 // conv_chain.cuh -- a whole ResNet stage (up to CH_MAX_LAYERS convolutions) as ONE persistent launch of the
-// tcgen05 implicit-GEMM convolution (conv_gemm.cuh), with image-granular dataflow between the layers.
+// tcgen05 implicit-GEMM convolution (conv_gemm.cuh), with tile-granular dataflow between the layers.
+// EXPERIMENTAL: off unless MRCNN_CHAIN=1; bit-identical to the layer-by-layer launches, not faster yet.
 //
 // Why: at batch 8 the res3..res5 layers have only 64..256 M tiles for 148 SMs.  Launched one by one, every layer
 // pays a partial last round (256 tiles = 1.73 rounds) and a launch head + tail of ~5 us out of its 25..40 us
@@ -15,10 +16,15 @@
 //                a serial chain of layers with only 16 items per layer, and the 74 pairs starve: 22 % of the producer
 //                time was spent spinning, tools/chain_stats.py.)
 //
+// Roles of a CTA (8 warps): TMA producer, MMA issuer (leader CTA of the pair), four epilogue warps that only compute,
+// a store thread (TMA stores of the staged chunks, buffer hand-back, residual prefetch) and a signal thread (the
+// gpu-scope release-increment of the counters costs ~1 us: on its own thread it delays nothing else; the store thread
+// tells it which store groups have been written, cp.async.bulk.wait_group being per thread).
+//
 // Deadlock freedom: every role of every CTA processes its items in list order, a wait only ever refers to items
 // that come EARLIER in the list, all CTAs are co-resident (grid <= cudaOccupancyMaxActiveClusters), and the only
-// thread that blocks on a flag is the producer (the epilogue's residual prefetch is skipped, not blocked, while the
-// producer has not yet passed the dependency check of that item).
+// thread that blocks on a counter is the producer (the store thread's residual prefetch polls the producer's progress
+// word and is skipped, not blocked, while the producer has not yet passed the dependency check of that item).
 // Write-after-read safety of the activation buffers follows from the same per-tile chains provided the output of the
 // layer in front of a 3x3 convolution is double-buffered across blocks (pipeline.cu); stages are separate
 // launches because the buffer geometry changes between them.
@@ -43,22 +49,22 @@
 #define CH_STAT_P_EMPTY 2      // producer: waiting for a free ring slot
 #define CH_STAT_M_FULL 3       // MMA: waiting for operands
 #define CH_STAT_M_TEMPTY 4     // MMA: waiting for a drained accumulator
-#define CH_STAT_E_TFULL 5      // epilogue (thread e0): waiting for a finished accumulator
-#define CH_STAT_E_RFULL 6      // epilogue (e0): waiting for a residual chunk
-#define CH_STAT_E_BULK 7       // epilogue (e0): in cp.async.bulk.wait_group
+#define CH_STAT_E_TFULL 5      // epilogue (first thread): waiting for a finished accumulator
+#define CH_STAT_E_RFULL 6      // epilogue (first thread): waiting for a residual chunk
+#define CH_STAT_E_BULK 7       // store thread: in cp.async.bulk.wait_group
 #define CH_STAT_E_ITEMS 8      // items processed by this CTA
 #define CH_STAT_E_CHUNKS 9
 #define CH_STAT_E_FLUSH 10     // flushes of pending signals before an idle wait
 #define CH_STAT_P_SPINS 11     // producer: items that had to spin at least once
-#define CH_STAT_E_SERIAL 12    // epilogue (e0): store issue + residual prefetch + signalling (the other 127 threads run ahead meanwhile)
-#define CH_STAT_E_BARRIER 13   // epilogue (e0): in bar.sync (waiting for the other epilogue threads)
-#define CH_STAT_E_SIGNAL 14    // epilogue (e0): inside fire_signals
+#define CH_STAT_E_SERIAL 12    // store thread: busy storing a chunk (store issue, hand-back, publishing completed groups)
+#define CH_STAT_E_BARRIER 13   // epilogue (first thread): waiting for a staging buffer to be handed back
+#define CH_STAT_E_SIGNAL 14    // signal thread: inside the release-increments
 #define CH_THREADS 256             // producer, MMA, 4 epilogue warps, store warp, signal warp
 #define CH_SIGQ 16                 // completion-signal queue entries (store thread -> signal thread)
 #define CH_SMEM_BYTES (1024 + CH_STAGES * CH_STAGE_BYTES + CH_NBUF * CH_OUT_BYTES + 512)
 
 struct ChainLayer {               // 64 bytes, lives in the kernel parameter (constant bank)
-  uint32_t item_end_unused;
+  uint32_t reserved;
   uint16_t tiles_x, tiles_y, tiles_n, tiles_per_img;
   uint16_t cout, bn, cin_chunks;
   uint8_t ntaps, stride, tw, th, relu, res;

@@ -11,8 +11,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import maskrcnn_b200 as m
 
-NAMES = ["total", "prod:flags", "prod:ring-empty", "mma:operands", "mma:acc-busy", "epi:acc-wait", "epi:residual", "epi:bulk-wait",
-         "items", "chunks", "flushes", "prod:items-spun", "epi:e0-serial", "epi:bar.sync", "epi:signals", "-"]
+NAMES = ["total", "prod:flags", "prod:ring-empty", "mma:operands", "mma:acc-busy", "epi:acc-wait", "epi:residual", "store:bulk-wait",
+         "items", "chunks", "flushes", "prod:items-spun", "store:busy", "epi:buffer-wait", "signal:release", "-"]
 
 
 def main():
