@@ -192,7 +192,11 @@ def run_reference(args):
     emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": workload, "image": "1024x1024", "rois": 1000},
+        "dtype": "f32", "data": "synthetic",
+        # the same workload as the B200 arm's `config` (one image of that batch per step: a bounded sample)
+        "config": {"workload": workload, "image": "1024x1024x3", "batch_per_gpu": args.batch, "global_batch": args.batch * max(args.gpus, 1),
+                   "pre_nms": 6000, "rois": 1000, "detections": 100,
+                   "model": "ResNet101+FPN Mask-RCNN, 81 classes, synthetic fp16 weights (seed 7)", "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": kind_cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
