@@ -55,3 +55,25 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".swift")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "liboracle" not in src and "from oracle" not in src and "import oracle" not in src, f
+
+
+def test_header_is_plain_c_and_example_links(tmp_path):
+    """include/maskrcnn_cuda.h is what a Swift module map / cgo / JNI stub consumes: it must compile as strict C99, and the
+    C example (examples/predict.c: the streaming calls + decode) must link against the library.  Running it here (no GPU,
+    no products) must fail loudly through the status / mrcnn_last_error path, never crash."""
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "predict_example")
+    libdir = os.path.join(root, "mask-rcnn-coreml_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "examples", "predict.c"), "-L" + libdir, "-lmaskrcnn_cuda", "-o", exe])
+    env = dict(os.environ, LD_LIBRARY_PATH=libdir + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([exe, str(tmp_path), "1", "1"], env=env, capture_output=True, text=True, timeout=120)
+    import torch
+    if not torch.cuda.is_available():
+        assert r.returncode == 1 and "mrcnn_create failed" in r.stderr and len(r.stderr.strip()) > len("mrcnn_create failed (-2):")
