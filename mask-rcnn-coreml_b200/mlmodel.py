@@ -41,6 +41,8 @@ VARINT, I64, LEN, I32 = 0, 1, 2, 5
 def _read_varint(buf, pos):
     result = shift = 0
     while True:
+        if pos >= len(buf):
+            raise ValueError("truncated varint")
         b = buf[pos]
         pos += 1
         result |= (b & 0x7F) << shift
@@ -61,6 +63,8 @@ def parse_message(buf):
         if wt == VARINT:
             v, pos = _read_varint(buf, pos)
         elif wt == I64:
+            if pos + 8 > n:
+                raise ValueError("truncated 64-bit field")
             v = struct.unpack_from("<Q", buf, pos)[0]
             pos += 8
         elif wt == LEN:
@@ -70,6 +74,8 @@ def parse_message(buf):
             v = buf[pos:pos + ln]
             pos += ln
         elif wt == I32:
+            if pos + 4 > n:
+                raise ValueError("truncated 32-bit field")
             v = struct.unpack_from("<I", buf, pos)[0]
             pos += 4
         else:
@@ -126,6 +132,38 @@ def _all(fields, number):
     return [v for f, _, v in fields if f == number]
 
 
+def _uint(fields, number, default=0):
+    """first varint occurrence of a scalar field (other wire types under that number are ignored)."""
+    for f, wt, v in fields:
+        if f == number and wt == VARINT:
+            return v
+    return default
+
+
+def _float(fields, number, default=None):
+    """first 32-bit occurrence of a float field."""
+    for f, wt, v in fields:
+        if f == number and wt == I32:
+            return _f32(v)
+    return default
+
+
+def _text(fields, number):
+    """first length-delimited occurrence of a string field, decoded ('' when absent or of another wire type)."""
+    for f, wt, v in fields:
+        if f == number and wt == LEN:
+            return bytes(v).decode()
+    return ""
+
+
+def _sub(fields, number):
+    """first length-delimited occurrence of a sub-message field, or None (a scalar with that number is not a message)."""
+    for f, wt, v in fields:
+        if f == number and wt == LEN:
+            return v
+    return None
+
+
 def _repeated_u64(fields, number):
     """repeated uint64: packed (LEN) or unpacked (VARINT) encodings."""
     out = []
@@ -134,7 +172,7 @@ def _repeated_u64(fields, number):
             continue
         if wt == VARINT:
             out.append(v)
-        else:
+        elif wt == LEN:
             pos = 0
             while pos < len(v):
                 x, pos = _read_varint(v, pos)
@@ -154,20 +192,24 @@ def _weights(msg):
     if msg is None:
         return None
     f = parse_message(msg)
-    h = _first(f, 2)
+    h = _sub(f, 2)
     if h is not None and len(h):
+        if len(h) % 2:
+            raise ValueError("float16Value of odd length")
         return np.frombuffer(h, dtype="<f2").astype(np.float32)
     vals = []
     for num, wt, v in f:
         if num != 1:
             continue
         if wt == LEN:
+            if len(v) % 4:
+                raise ValueError("packed floatValue of a length that is not a multiple of 4")
             vals.append(np.frombuffer(v, dtype="<f4"))
-        else:
+        elif wt == I32:
             vals.append(np.array([_f32(v)], np.float32))
     if vals:
         return np.concatenate(vals).astype(np.float32)
-    raw = _first(f, 30)
+    raw = _sub(f, 30)
     if raw is not None and len(raw):
         raise ValueError("quantised (rawValue) weights are not supported")
     return None
@@ -175,50 +217,53 @@ def _weights(msg):
 
 def _layer(msg):
     f = parse_message(msg)
-    L = {"name": bytes(_first(f, 1, b"")).decode(), "inputs": [bytes(x).decode() for x in _all(f, 2)],
-         "outputs": [bytes(x).decode() for x in _all(f, 3)], "type": "other"}
-    conv, ip, bn, custom = _first(f, 100), _first(f, 140), _first(f, 160), _first(f, 500)
+    L = {"name": _text(f, 1), "inputs": [bytes(v).decode() for n, wt, v in f if n == 2 and wt == LEN],
+         "outputs": [bytes(v).decode() for n, wt, v in f if n == 3 and wt == LEN], "type": "other"}
+    conv, ip, bn, custom = _sub(f, 100), _sub(f, 140), _sub(f, 160), _sub(f, 500)
     if conv is not None:
         c = parse_message(conv)
         ks = _repeated_u64(c, 20) or [3, 3]
         st = _repeated_u64(c, 30) or [1, 1]
-        cout, kc, groups = _first(c, 1, 0), _first(c, 2, 0), _first(c, 10, 1) or 1
-        deconv = bool(_first(c, 60, 0))
-        w = _weights(_first(c, 90))
+        cout, kc, groups = _uint(c, 1), _uint(c, 2), _uint(c, 10, 1) or 1
+        deconv = bool(_uint(c, 60))
+        w = _weights(_sub(c, 90))
+        if len(ks) < 2 or len(st) < 2:
+            raise ValueError("convolution without a 2-D kernel size / stride")
         shape = (kc, cout // groups, ks[0], ks[1]) if deconv else (cout, kc, ks[0], ks[1])
         L.update(type="deconvolution" if deconv else "convolution", cout=cout, kernel_channels=kc, groups=groups,
-                 kernel_size=tuple(ks), stride=tuple(st), padding="same" if _first(c, 51) is not None else "valid",
+                 kernel_size=tuple(ks), stride=tuple(st), padding="same" if _sub(c, 51) is not None else "valid",
                  weights=None if w is None else w.reshape(shape),
-                 bias=_weights(_first(c, 91)) if _first(c, 70, 0) else None)
+                 bias=_weights(_sub(c, 91)) if _uint(c, 70) else None)
     elif ip is not None:
         c = parse_message(ip)
-        cin, cout = _first(c, 1, 0), _first(c, 2, 0)
-        w = _weights(_first(c, 20))
+        cin, cout = _uint(c, 1), _uint(c, 2)
+        w = _weights(_sub(c, 20))
         L.update(type="innerProduct", cin=cin, cout=cout, weights=None if w is None else w.reshape(cout, cin),
-                 bias=_weights(_first(c, 21)) if _first(c, 10, 0) else None)
+                 bias=_weights(_sub(c, 21)) if _uint(c, 10) else None)
     elif bn is not None:
         c = parse_message(bn)
-        eps = _first(c, 10)
-        L.update(type="batchnorm", channels=_first(c, 1, 0), epsilon=_f32(eps) if eps is not None else 1e-5,
-                 gamma=_weights(_first(c, 15)), beta=_weights(_first(c, 16)), mean=_weights(_first(c, 17)),
-                 variance=_weights(_first(c, 18)))
+        L.update(type="batchnorm", channels=_uint(c, 1), epsilon=_float(c, 10, 1e-5),
+                 gamma=_weights(_sub(c, 15)), beta=_weights(_sub(c, 16)), mean=_weights(_sub(c, 17)),
+                 variance=_weights(_sub(c, 18)))
     elif custom is not None:
         c = parse_message(custom)
         params = {}
-        for entry in _all(c, 30):                 # map<string, CustomLayerParamValue> = repeated {key=1, value=2}
+        for n30, wt30, entry in c:                # map<string, CustomLayerParamValue> = repeated {key=1, value=2}
+            if n30 != 30 or wt30 != LEN:
+                continue
             e = parse_message(entry)
-            k = bytes(_first(e, 1, b"")).decode()
-            v = parse_message(_first(e, 2, b""))
+            k = _text(e, 1)
+            v = parse_message(_sub(e, 2) or b"")
             for num, wt, x in v:
-                if num == 10:
+                if num == 10 and wt == I64:
                     params[k] = struct.unpack("<d", struct.pack("<Q", x))[0]
-                elif num == 20:
+                elif num == 20 and wt == LEN:
                     params[k] = bytes(x).decode()
-                elif num in (30, 40):
+                elif num in (30, 40) and wt == VARINT:
                     params[k] = x - (1 << 64) if x >> 63 else x
-                elif num == 50:
+                elif num == 50 and wt == VARINT:
                     params[k] = bool(x)
-        L.update(type="custom", class_name=bytes(_first(c, 10, b"")).decode(), parameters=params)
+        L.update(type="custom", class_name=_text(c, 10), parameters=params)
     return L
 
 
@@ -230,20 +275,23 @@ def read_mlmodel(data):
     top = parse_message(data)
     nn = None
     for num in (500, 403, 303):
-        nn = _first(top, num)
+        nn = _sub(top, num)
         if nn is not None:
             break
     if nn is None:
         raise ValueError("not a neural-network Core ML model (no field 500 / 403 / 303)")
     f = parse_message(nn)
     pre = {}
-    for p in _all(f, 2):
-        sc = _first(parse_message(p), 10)
+    for n2, wt2, p in f:
+        if n2 != 2 or wt2 != LEN:
+            continue
+        sc = _sub(parse_message(p), 10)
         if sc is not None:
             s = parse_message(sc)
-            g = lambda n, d: _f32(_first(s, n)) if _first(s, n) is not None else d
+            g = lambda n, d: _float(s, n, d)
             pre = {"channelScale": g(10, 1.0), "blueBias": g(20, 0.0), "greenBias": g(21, 0.0), "redBias": g(22, 0.0)}
-    return {"specification_version": _first(top, 1, 0), "layers": [_layer(m) for m in _all(f, 1)], "preprocessing": pre}
+    return {"specification_version": _uint(top, 1), "layers": [_layer(m) for n1, wt1, m in f if n1 == 1 and wt1 == LEN],
+            "preprocessing": pre}
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -126,3 +126,60 @@ def test_wire_format_matches_google_protobuf(pkg):
         np.testing.assert_array_equal(back["layers"][0]["bias"], b)
         assert back["layers"][0]["kernel_size"] == (3, 3) and back["layers"][0]["padding"] == "same"
         np.testing.assert_array_equal(back["layers"][1]["variance"], var)
+
+
+def test_parser_rejects_garbage_cleanly(pkg):
+    """Random bytes and byte mutations of a small model that exercises every layer kind either parse or raise
+    ValueError / KeyError -- never another exception type (wrong wire types under known field numbers, truncated
+    scalars, odd-length weight blobs ...), never a hang."""
+    rng = np.random.default_rng(11)
+    w = rng.standard_normal((8, 4, 3, 3)).astype(np.float32)
+    b = rng.standard_normal(8).astype(np.float32)
+    layers = [{"name": "c", "type": "convolution", "inputs": ["x"], "outputs": ["y"], "cout": 8, "kernel_channels": 4, "kernel_size": (3, 3),
+               "stride": (1, 1), "padding": "same", "weights": w, "bias": b},
+              {"name": "d", "type": "deconvolution", "inputs": ["x"], "outputs": ["y"], "cout": 8, "kernel_channels": 4, "kernel_size": (2, 2),
+               "stride": (2, 2), "padding": "valid", "weights": rng.standard_normal((4, 8, 2, 2)).astype(np.float32), "bias": b},
+              {"name": "bn", "type": "batchnorm", "inputs": ["y"], "outputs": ["z"], "channels": 8, "epsilon": 1e-3, "gamma": b, "beta": b, "mean": b, "variance": b * b},
+              {"name": "fc", "type": "innerProduct", "inputs": ["z"], "outputs": ["o"], "cin": 4, "cout": 8, "weights": rng.standard_normal((8, 4)).astype(np.float32), "bias": b},
+              {"name": "p", "type": "custom", "inputs": [], "outputs": [], "class_name": "ProposalLayer",
+               "parameters": {"maxProposals": 1000, "thr": 0.7, "s": "x", "flag": True}}]
+    parsed = 0
+    for half in (True, False):
+        src = pkg.mlmodel.write_mlmodel(layers, {"redBias": -1.0}, half)
+        back = pkg.mlmodel.read_mlmodel(src)
+        assert [L["type"] for L in back["layers"]] == [L["type"] for L in layers]
+        assert back["layers"][4]["parameters"] == layers[4]["parameters"] and back["preprocessing"]["redBias"] == -1.0
+        cases = [bytes(rng.integers(0, 256, int(n), dtype=np.uint8)) for n in rng.integers(1, 200, 50)]
+        cases += [src[:int(k)] for k in rng.integers(1, len(src), 50)]
+        for _ in range(3000):
+            m = bytearray(src)
+            for pos in rng.integers(0, len(m), int(rng.integers(1, 6))):
+                m[int(pos)] = int(rng.integers(0, 256))
+            cases.append(bytes(m))
+        for data in cases:
+            try:
+                pkg.mlmodel.read_mlmodel(data)
+                parsed += 1
+            except (ValueError, KeyError):
+                pass
+    assert parsed > 1000          # most single-byte mutations land in weight payloads and still parse
+
+
+def test_import_cli_writes_products(pkg, exported, tmp_path):
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = ("MaskRCNN.mlmodel", "Classifier.mlmodel", "Mask.mlmodel")
+    for n, data in zip(names, exported[2]):
+        (tmp_path / n).write_bytes(data)
+    out = tmp_path / "products"
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "import_mlmodel.py"), "--main", str(tmp_path / names[0]),
+                           "--classifier", str(tmp_path / names[1]), "--mask", str(tmp_path / names[2]), "--architecture", "50",
+                           "--out", str(out), "--anchors"], stdout=subprocess.DEVNULL)
+    want = pkg.weights.fold(exported[0], 50)
+    for which, n in enumerate(("MaskRCNN", "Classifier", "Mask")):
+        blob = (out / (n + ".mrcnnw")).read_bytes()
+        assert blob == pkg.weights.pack_blob(which, pkg.weights.device_tensors(want, which, 50))
+    anchors = np.fromfile(out / "anchors.bin", np.float32).reshape(-1, 4)
+    assert anchors.shape[0] == 261888 and (anchors == pkg.synth.generate_anchors(1024, 1024)).all()      # Conversion/task.py:176
