@@ -77,3 +77,26 @@ def test_header_is_plain_c_and_example_links(tmp_path):
     import torch
     if not torch.cuda.is_available():
         assert r.returncode == 1 and "mrcnn_create failed" in r.stderr and len(r.stderr.strip()) > len("mrcnn_create failed (-2):")
+
+
+def test_swift_and_cpp_bindings_only_use_declared_symbols():
+    """The Swift sources cannot be compiled here (no toolchain): at least every mrcnn_* identifier they (and the C++
+    mirror, which IS compiled) use must be declared in include/maskrcnn_cuda.h, every struct field they set must exist,
+    and the five @objc layer classes of the reference must all be bound."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "maskrcnn_cuda.h")).read()
+    declared = set(re.findall(r"\b(mrcnn_[a-z0-9_]+)\s*\(", header)) | {"mrcnn_config", "mrcnn_ctx", "mrcnn_status"}
+    fields = set(re.findall(r"\b([a-z_0-9]+)(?:\[\d\])?\s*[;,]", header[header.index("typedef struct mrcnn_config"):header.index("} mrcnn_config;")]))
+    swift_dir = os.path.join(root, "swift", "Sources", "MaskRCNNCuda")
+    sources = {f: open(os.path.join(swift_dir, f)).read() for f in os.listdir(swift_dir) if f.endswith(".swift")}
+    sources["maskrcnn.hpp"] = open(os.path.join(root, "include", "maskrcnn.hpp")).read()
+    for name, text in sources.items():
+        used = set(re.findall(r"\b(mrcnn_[a-z0-9_]+)\b", text)) - {"mrcnn_status"}
+        assert used <= declared, f"{name} uses undeclared symbols: {sorted(used - declared)}"
+        if name.endswith(".swift"):
+            for f in re.findall(r"\bcfg\.([a-z_0-9]+)", text):
+                assert f in fields, f"{name} sets mrcnn_config.{f}, which the header does not declare"
+    objc = set(re.findall(r"@objc\((\w+)\)", "".join(t for n, t in sources.items() if n.endswith(".swift"))))
+    assert objc == {"ProposalLayer", "PyramidROIAlignLayer", "TimeDistributedClassifierLayer", "DetectionLayer", "TimeDistributedMaskLayer"}
