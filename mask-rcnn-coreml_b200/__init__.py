@@ -7,4 +7,4 @@ from ._cabi import MaskRCNNError, LIB_PATH, lib  # noqa: F401
 from .layers import (Context, DetectionLayer, ProposalLayer, PyramidROIAlignLayer,  # noqa: F401
                      TimeDistributedClassifierLayer, TimeDistributedMaskLayer, default_context)
 from .model import Detection, MaskRCNN, MaskRCNNConfig  # noqa: F401
-from . import distributed, h5lite, keras_h5, mlmodel, results_pb, synth, weights  # noqa: F401
+from . import coco, distributed, h5lite, keras_h5, mlmodel, results_pb, synth, weights  # noqa: F401
