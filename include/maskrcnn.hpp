@@ -179,6 +179,16 @@ class Context {
     if (status != MRCNN_OK) throw Error(status, mrcnn_last_error(ctx_));
   }
   void setAnchors(const float* anchors, std::int64_t n) { check(mrcnn_set_anchors(ctx_, anchors, n)); }
+  // anchors for the configured image size, generated on demand instead of read from anchors.bin (the reference's
+  // own TODO, MaskRCNNConfig.swift:14)
+  void generateAnchors() {
+    const std::int64_t n = mrcnn_anchor_count(c_.image_h, c_.image_w);
+    if (n < 0) throw Error(static_cast<int>(n), "mrcnn_anchor_count: bad image size");
+    std::vector<float> a(static_cast<size_t>(n) * 4);
+    int st = mrcnn_generate_anchors(c_.image_h, c_.image_w, a.data(), n);
+    if (st != MRCNN_OK) throw Error(st, "mrcnn_generate_anchors failed");
+    setAnchors(a.data(), n);
+  }
   // which: 0 = MaskRCNN (backbone + FPN + RPN), 1 = Classifier, 2 = Mask
   void setWeights(int which, const void* blob, size_t bytes) { check(mrcnn_set_weights(ctx_, which, blob, bytes)); }
   void setStream(void* cuda_stream) { check(mrcnn_set_stream(ctx_, cuda_stream)); }
@@ -521,7 +531,9 @@ class MaskRCNN {
   };
 
   explicit MaskRCNN(const MaskRCNNConfig& configuration = MaskRCNNConfig::defaultConfig())
-      : ctx_(std::make_shared<Context>(configuration)) {}
+      : ctx_(std::make_shared<Context>(configuration)) {
+    if (!configuration.anchorsURL) ctx_->generateAnchors();  // no anchors.bin configured: generated for the input size
+  }
   explicit MaskRCNN(ContextRef ctx) : ctx_(std::move(ctx)) {
     if (!ctx_) throw Error(MRCNN_EINVAL, "MaskRCNN needs a context");
   }

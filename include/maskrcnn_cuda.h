@@ -135,6 +135,15 @@ MRCNN_API int mrcnn_synchronize(mrcnn_ctx* ctx);
 MRCNN_API int mrcnn_set_anchors(mrcnn_ctx* ctx, const float* anchors, int64_t num_anchors);
 MRCNN_API int mrcnn_set_weights(mrcnn_ctx* ctx, int which, const void* blob, size_t bytes);
 MRCNN_API int64_t mrcnn_num_anchors(const mrcnn_ctx* ctx);
+/* Anchors on demand instead of the pre-computed anchors.bin (the reference's own TODO, MaskRCNNConfig.swift:14:
+ * "generate the anchors on demand based on image shape, this will save 5mb").  Host arithmetic, no device needed:
+ * the Matterport rule of the reference's conversion package (scales 32..512 on strides 4..64, ratios 0.5/1/2,
+ * level-major then y, x, ratio; normalised (y1,x1,y2,x2)), i.e. the content Conversion/task.py:176 writes.
+ * mrcnn_anchor_count: N for an image size (261 888 at 1024x1024, 65 472 at 512x512), negative status when < 2 pixels.
+ * mrcnn_generate_anchors: writes N x 4 floats; capacity = number of ROWS anchors_out can hold.  Pass the result to
+ * mrcnn_set_anchors. */
+MRCNN_API int64_t mrcnn_anchor_count(int image_h, int image_w);
+MRCNN_API int mrcnn_generate_anchors(int image_h, int image_w, float* anchors_out, int64_t capacity);
 
 /* ---- ProposalLayer -----------------------------------------------------
  * outputShapes (ProposalLayer.swift:97-101): (max_proposals, 4). */

@@ -55,6 +55,8 @@ SIGNATURES = {
     "mrcnn_set_anchors": (_i, [_vp, _vp, _i64]),
     "mrcnn_set_weights": (_i, [_vp, _i, _vp, C.c_size_t]),
     "mrcnn_num_anchors": (_i64, [_vp]),
+    "mrcnn_anchor_count": (_i64, [_i, _i]),
+    "mrcnn_generate_anchors": (_i, [_i, _i, _vp, _i64]),
     "mrcnn_proposal_output_shape": (_i, [_vp, C.POINTER(_i64)]),
     "mrcnn_proposal_eval": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
     "mrcnn_pyramid_roialign_output_shape": (_i, [_vp, _i64, _i64, _i, C.POINTER(_i64)]),

@@ -66,6 +66,20 @@ class Context:
         a = np.ascontiguousarray(anchors, dtype=np.float32).reshape(-1, 4)
         check(self.handle, lib().mrcnn_set_anchors(self.handle, ptr(a), a.shape[0]))
 
+    def generate_anchors(self):
+        """Anchors for the configured image size, generated on demand instead of read from anchors.bin (the reference's own
+        TODO, MaskRCNNConfig.swift:14); mrcnn_generate_anchors + mrcnn_set_anchors.  Returns the (N,4) array."""
+        l = lib()
+        n = l.mrcnn_anchor_count(self.cfg.image_h, self.cfg.image_w)
+        if n < 0:
+            raise MaskRCNNError(int(n), "mrcnn_anchor_count: bad image size")
+        a = np.empty((n, 4), np.float32)
+        st = l.mrcnn_generate_anchors(self.cfg.image_h, self.cfg.image_w, ptr(a), n)
+        if st != 0:
+            raise MaskRCNNError(st, "mrcnn_generate_anchors failed")
+        self.set_anchors(a)
+        return a
+
     def set_weights(self, which, blob):
         buf = bytes(blob)
         check(self.handle, lib().mrcnn_set_weights(self.handle, which, buf, len(buf)))

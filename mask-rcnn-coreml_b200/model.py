@@ -91,6 +91,8 @@ class MaskRCNN:
         self.ctx = Context(**ov)
         if anchors is not None:
             self.ctx.set_anchors(anchors)
+        elif cfg.anchorsURL is None:
+            self.ctx.generate_anchors()            # no anchors.bin configured: generated for the model's input size
         if blobs is not None:                      # in-memory weights instead of files
             for which, blob in enumerate(blobs):
                 self.ctx.set_weights(which, blob)

@@ -100,3 +100,22 @@ def test_swift_and_cpp_bindings_only_use_declared_symbols():
                 assert f in fields, f"{name} sets mrcnn_config.{f}, which the header does not declare"
     objc = set(re.findall(r"@objc\((\w+)\)", "".join(t for n, t in sources.items() if n.endswith(".swift"))))
     assert objc == {"ProposalLayer", "PyramidROIAlignLayer", "TimeDistributedClassifierLayer", "DetectionLayer", "TimeDistributedMaskLayer"}
+
+
+def test_anchor_generation_matches_the_python_generator():
+    """mrcnn_generate_anchors (host arithmetic, the reference's "generate the anchors on demand" TODO) is bit-identical to
+    synth.generate_anchors, i.e. to the anchors.bin content the tests and the bench use."""
+    import ctypes as C
+    import numpy as np
+    import maskrcnn_b200 as m
+    l = m.lib()
+    for h, w, n in ((1024, 1024, 261888), (512, 512, 65472), (256, 256, 16368), (128, 128, 4092), (640, 384, None), (100, 70, None)):
+        want = m.synth.generate_anchors(h, w)
+        cnt = l.mrcnn_anchor_count(h, w)
+        assert cnt == want.shape[0] and (n is None or cnt == n)
+        got = np.full((cnt + 1, 4), 7.0, np.float32)
+        assert l.mrcnn_generate_anchors(h, w, got.ctypes.data_as(C.c_void_p), cnt) == 0
+        np.testing.assert_array_equal(got[:cnt], want)
+        assert (got[cnt] == 7.0).all()                                   # nothing written past N rows
+        assert l.mrcnn_generate_anchors(h, w, got.ctypes.data_as(C.c_void_p), cnt - 1) == m._cabi.EINVAL
+    assert l.mrcnn_anchor_count(1, 1024) == m._cabi.EINVAL and l.mrcnn_generate_anchors(1024, 1024, None, 1 << 20) == m._cabi.EINVAL

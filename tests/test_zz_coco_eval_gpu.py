@@ -21,3 +21,23 @@ def test_evaluate_dataset_on_the_real_model_gpu(pkg, tmp_path):
                 assert d["probability"] > 0.7 and d["classId"] >= 1 and d["classLabel"] == "test"
     finally:
         model.close()
+
+
+def test_anchors_generated_on_demand_gpu(pkg):
+    """No anchors.bin configured: MaskRCNN generates the anchors for its input size (mrcnn_generate_anchors, the reference's
+    own TODO) -- same predictions as with the anchors passed in."""
+    import numpy as np
+    cfg = pkg.MaskRCNNConfig()
+    cfg.architecture, cfg.imageShape, cfg.preNMSMaxProposals, cfg.maxProposals, cfg.maxBatch = "resnet50", (256, 256, 3), 1000, 200, 2
+    _, blobs = pkg.weights.synthetic_blobs(50)
+    img = np.random.default_rng(20260).integers(0, 256, (256, 256, 3), dtype=np.uint8)
+    a = pkg.MaskRCNN(cfg, blobs=blobs)
+    b = pkg.MaskRCNN(cfg, blobs=blobs, anchors=pkg.synth.generate_anchors(256, 256))
+    try:
+        assert int(pkg.lib().mrcnn_num_anchors(a.ctx.handle)) == 16368
+        oa, ob = a.prediction(img), b.prediction(img)
+        np.testing.assert_array_equal(oa["detections"], ob["detections"])
+        np.testing.assert_array_equal(oa["mask"], ob["mask"])
+    finally:
+        a.close()
+        b.close()
