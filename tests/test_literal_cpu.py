@@ -234,3 +234,40 @@ def test_mask_layer_and_decode_literal_equal_oracle(orc):
         assert i == idx[k] and c == dc[k] and sc == score[k]
         np.testing.assert_array_equal(np.array(box), bbox[k])
         np.testing.assert_array_equal(mask, mu8[k])
+
+
+def test_literal_model_reproduces_the_committed_golden_fixtures():
+    """tests/golden/*.npz were generated with oracle.c (make_golden.py) and are what the CUDA path is compared with on the
+    GPU; the literal model of the Swift sources must give the same arrays, so the fixtures rest on both restatements."""
+    import os
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(G, "proposal.npz"))
+    for pk, rk, kk, ck in (("probs", "rois", "keep", "count"), ("tie_probs", "tie_rois", "tie_keep", "tie_count")):
+        out, ri, order = lit.proposal_evaluate(g[pk], g["deltas"], g["anchors"], pre_nms=600, max_proposals=100, fix_q4=True)
+        cnt = int(g[ck])
+        assert len(ri) == cnt
+        np.testing.assert_array_equal(out, g[rk])
+        np.testing.assert_array_equal(order[ri].astype(np.int32), g[kk][:cnt])
+    g = np.load(os.path.join(G, "roialign.npz"))
+    maps = [g[f"maps{i}"] for i in range(4)]
+    for pool, key, rois in ((7, "pooled7", g["rois"]), (14, "pooled14", np.concatenate([g["rois"], np.zeros((64, 2), np.float32)], axis=1))):
+        out, written = lit.pyramid_roialign_evaluate(rois, maps, pool, 1024.0, 1024.0)
+        np.testing.assert_array_equal(out[written], g[key][written])
+        assert (g[key][~written] == 0).all() and written.mean() > 0.8
+    items = lit.rois_to_input_items(g["rois"], 224.0, 1024.0, 1024.0)
+    np.testing.assert_array_equal(np.array([c[0] + 2 if c is not None else -1 for _, c in items], np.int32), g["levels"])
+    g = np.load(os.path.join(G, "detection.npz"))
+    out, idx = lit.detection_evaluate(g["rois"], g["cls"])
+    cnt = int(g["count"])
+    np.testing.assert_array_equal(out, g["det"])
+    np.testing.assert_array_equal(np.array(idx, np.int32), g["keep"][:cnt])
+    m = np.load(os.path.join(G, "mask_decode.npz"))
+    sel = lit.mask_evaluate(np.where(m["valid"][:, None, None, None] > 0, np.float32(1), np.float32(0)) * np.ones((100, 1, 2, 2), np.float32),
+                            g["det"], lambda i: m["masks_all"][i])
+    np.testing.assert_array_equal(sel, m["selected"])
+    ref = lit.detections_from_feature_value(g["det"], m["masks"].astype(np.float64))
+    assert len(ref) == int(m["n"])
+    for k, (i, box, c, sc, mask) in enumerate(ref):
+        assert i == m["index"][k] and c == m["classes"][k] and sc == m["score"][k]
+        np.testing.assert_array_equal(np.array(box), m["bbox"][k])
+        np.testing.assert_array_equal(mask, m["mask_u8"][k])
