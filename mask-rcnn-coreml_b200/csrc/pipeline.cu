@@ -223,6 +223,41 @@ static int add_stage(mrcnn_ctx* ctx, Graph& g, int stage_index, const std::vecto
   return MRCNN_OK;
 }
 
+// Experiment knob (off by default): MRCNN_STAGE_SPLIT is a bit mask of the ResNet stages (bit 0 =
+// res2 ... bit 3 = res5) whose layers are launched per HALF batch -- all blocks of the stage for images [0, B/2), then
+// for images [B/2, B) -- so that one block's working set fits the L2 (res4 at batch 8: 170 MB -> 85 MB).  The launches
+// are derived from the full-batch ones by narrowing `n` and advancing the image-major NHWC pointers; tiles never span
+// images, so the results are bit-identical.
+static int stage_split_parts(int stage_index, int B) {
+  const char* e = getenv("MRCNN_STAGE_SPLIT");
+  if (!e || !((atoi(e) >> stage_index) & 1) || B < 2 || (B & 1)) return 1;
+  return 2;
+}
+
+static std::vector<ConvLaunch> split_stage_by_images(const std::vector<ConvLaunch>& layers, int B, int parts) {
+  std::vector<ConvLaunch> out;
+  const int nb = B / parts;
+  for (int k = 0; k < parts; ++k) {
+    for (const ConvLaunch& L0 : layers) {
+      ConvLaunch L = L0;
+      const size_t ld_in = (size_t)(L0.ld_in ? L0.ld_in : L0.cin);
+      const size_t ho = (size_t)(L0.h_out ? L0.h_out : (L0.h_in + 2 * L0.pad - L0.kh) / L0.stride + 1);
+      const size_t wo = (size_t)(L0.w_out ? L0.w_out : (L0.w_in + 2 * L0.pad - L0.kw) / L0.stride + 1);
+      const size_t ldc = (size_t)(L0.ldc ? L0.ldc : (L0.cout + 7) / 8 * 8);
+      const size_t img0 = (size_t)k * nb;
+      L.n = nb;
+      L.x = L0.x + img0 * L0.h_in * L0.w_in * ld_in;
+      L.out = (void*)((__half*)L0.out + img0 * ho * wo * ldc);
+      if (L0.residual) {
+        const size_t rh = (size_t)(L0.res_h ? L0.res_h : (int)ho), rw = (size_t)(L0.res_w ? L0.res_w : (int)wo);
+        L.residual = L0.residual + img0 * rh * rw * (size_t)(L0.res_ld ? L0.res_ld : (int)ldc);
+      }
+      out.push_back(L);
+    }
+  }
+  return out;
+}
+
 #define TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
 static inline int grid1d(int64_t total, int threads) { return (int)((total + threads - 1) / threads); }
@@ -341,6 +376,8 @@ static int build_backbone(mrcnn_ctx* ctx, int B, std::shared_ptr<Graph>* out_gra
       if (y == pp[cur ^ 1]) cur ^= 1;
       x = y; h = ho; w = wo; cin = 4 * f;
     }
+    const int parts = stage_split_parts(s, B);
+    if (parts > 1) stage_layers = split_stage_by_images(stage_layers, B, parts);
     TRY(add_stage(ctx, *g, s, stage_layers));
   }
   // ---- FPN
