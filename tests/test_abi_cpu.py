@@ -119,3 +119,29 @@ def test_anchor_generation_matches_the_python_generator():
         assert (got[cnt] == 7.0).all()                                   # nothing written past N rows
         assert l.mrcnn_generate_anchors(h, w, got.ctypes.data_as(C.c_void_p), cnt - 1) == m._cabi.EINVAL
     assert l.mrcnn_anchor_count(1, 1024) == m._cabi.EINVAL and l.mrcnn_generate_anchors(1024, 1024, None, 1 << 20) == m._cabi.EINVAL
+
+
+def test_anchor_rule_is_the_upstream_meshgrid_construction():
+    """The anchors (file content of anchors.bin, Conversion/task.py:176) against the upstream Matterport construction written
+    the way that package writes it (meshgrids of scales x ratios and of shifts; norm_boxes), SURVEY.md Appendix B."""
+    import numpy as np
+    import maskrcnn_b200 as m
+
+    def upstream(scales, ratios, shape, feature_stride, anchor_stride=1):
+        scales, ratios = np.meshgrid(np.array(scales), np.array(ratios))
+        scales, ratios = scales.flatten(), ratios.flatten()
+        heights, widths = scales / np.sqrt(ratios), scales * np.sqrt(ratios)
+        shifts_y = np.arange(0, shape[0], anchor_stride) * feature_stride
+        shifts_x = np.arange(0, shape[1], anchor_stride) * feature_stride
+        shifts_x, shifts_y = np.meshgrid(shifts_x, shifts_y)
+        box_widths, box_centers_x = np.meshgrid(widths, shifts_x)
+        box_heights, box_centers_y = np.meshgrid(heights, shifts_y)
+        box_centers = np.stack([box_centers_y, box_centers_x], axis=2).reshape([-1, 2])
+        box_sizes = np.stack([box_heights, box_widths], axis=2).reshape([-1, 2])
+        return np.concatenate([box_centers - 0.5 * box_sizes, box_centers + 0.5 * box_sizes], axis=1)
+
+    for h, w in ((1024, 1024), (512, 512), (640, 384)):
+        boxes = np.concatenate([upstream(s, (0.5, 1, 2), (int(np.ceil(h / st)), int(np.ceil(w / st))), st)
+                                for s, st in zip((32, 64, 128, 256, 512), (4, 8, 16, 32, 64))], axis=0)
+        norm = ((boxes - np.array([0, 0, 1, 1])) / np.array([h - 1, w - 1, h - 1, w - 1])).astype(np.float32)     # norm_boxes
+        np.testing.assert_array_equal(m.synth.generate_anchors(h, w), norm)
