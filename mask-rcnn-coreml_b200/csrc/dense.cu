@@ -95,7 +95,14 @@ int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan) {
   p.tiles_x = ceil_div(p.w_out, p.tw);
   p.tiles_y = ceil_div(p.h_out, p.th);
   int bn = L.bn;
-  if (!bn) bn = L.cout > 128 ? 256 : (L.cout > 64 ? 128 : (L.cout > 32 ? 64 : 32));
+  if (!bn) {
+    bn = L.cout > 128 ? 256 : (L.cout > 64 ? 128 : (L.cout > 32 ? 64 : 32));
+    // experiment knob (off unless set): MRCNN_CONV_BN=64|128 narrows the N tile of the layers that
+    // would use 256 (more, smaller tiles: finer wave quantisation against a lower MMA N), for per-layer A/B sweeps
+    static int env_bn = -1;
+    if (env_bn < 0) { const char* e = getenv("MRCNN_CONV_BN"); env_bn = e ? atoi(e) : 0; }
+    if ((env_bn == 64 || env_bn == 128) && bn == 256 && !L.deconv && !L.maskdot && !L.split_out) bn = env_bn;
+  }
   MRCNN_REQUIRE(ctx, bn == 32 || bn == 64 || bn == 128 || bn == 256, "conv: BN must be 32/64/128/256");
   if (L.deconv) MRCNN_REQUIRE(ctx, L.deconv_c % bn == 0 && L.cout == 4 * L.deconv_c, "conv: deconv needs deconv_c % BN == 0");
   p.tiles_n = ceil_div(L.cout, bn);
