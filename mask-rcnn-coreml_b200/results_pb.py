@@ -74,9 +74,12 @@ def result_from_detections(dataset_id, image_id, width, height, detections, clas
 
 
 # ---- minimal decoder (tests; also lets a Python consumer read the file without generated code) ----
+# Every malformed input raises ValueError (truncation, wrong wire type for a field, bad UTF-8, over-long varints).
 def _read_varint(buf, pos):
     shift = result = 0
     while True:
+        if pos >= len(buf) or shift > 63:
+            raise ValueError("Results: truncated or over-long varint")
         b = buf[pos]
         pos += 1
         result |= (b & 0x7F) << shift
@@ -93,42 +96,80 @@ def _fields(buf):
         if wt == 0:
             v, pos = _read_varint(buf, pos)
         elif wt == 1:
+            if pos + 8 > len(buf):
+                raise ValueError("Results: truncated double")
             v = struct.unpack_from("<d", buf, pos)[0]
             pos += 8
         elif wt == 2:
             n, pos = _read_varint(buf, pos)
+            if pos + n > len(buf):
+                raise ValueError("Results: truncated length-delimited field")
             v = bytes(buf[pos:pos + n])
             pos += n
         else:
-            raise ValueError(f"unsupported wire type {wt}")
+            raise ValueError(f"Results: unsupported wire type {wt}")
         yield field, wt, v
 
 
+def _want(wt, expected, what):
+    if wt != expected:
+        raise ValueError(f"Results: field {what} has wire type {wt}, expected {expected}")
+
+
+def _text(b):
+    try:
+        return b.decode("utf-8")
+    except UnicodeDecodeError:
+        raise ValueError("Results: string field is not UTF-8") from None
+
+
+def _to_int32(v):
+    v &= 0xFFFFFFFF
+    return v - (1 << 32) if v & 0x80000000 else v
+
+
 def decode_results(buf):
+    """Unknown fields are skipped, as protobuf parsers do."""
     out = []
-    for f, _, payload in _fields(buf):
+    for f, wt, payload in _fields(bytes(buf)):
         if f != 1:
             continue
+        _want(wt, 2, "Results.results")
         res = {"imageInfo": {"datasetId": "", "id": "", "width": 0, "height": 0}, "detections": []}
-        for f2, _, v in _fields(payload):
+        for f2, wt2, v in _fields(payload):
             if f2 == 1:
-                for f3, _, w in _fields(v):
-                    key = {1: "datasetId", 2: "id", 3: "width", 4: "height"}[f3]
-                    res["imageInfo"][key] = w.decode() if isinstance(w, bytes) else w
+                _want(wt2, 2, "Result.imageInfo")
+                for f3, wt3, w in _fields(v):
+                    if f3 in (1, 2):
+                        _want(wt3, 2, "ImageInfo string")
+                        res["imageInfo"]["datasetId" if f3 == 1 else "id"] = _text(w)
+                    elif f3 in (3, 4):
+                        _want(wt3, 0, "ImageInfo int32")
+                        res["imageInfo"]["width" if f3 == 3 else "height"] = _to_int32(w)
             elif f2 == 2:
+                _want(wt2, 2, "Result.detections")
                 d = {"probability": 0.0, "classId": 0, "classLabel": "", "boundingBox": {"x": 0.0, "y": 0.0, "width": 0.0, "height": 0.0}}
-                for f3, _, w in _fields(v):
+                for f3, wt3, w in _fields(v):
                     if f3 == 1:
+                        _want(wt3, 1, "Detection.probability")
                         d["probability"] = w
                     elif f3 == 2:
-                        d["classId"] = w
+                        _want(wt3, 0, "Detection.classId")
+                        d["classId"] = _to_int32(w)
                     elif f3 == 3:
-                        d["classLabel"] = w.decode()
+                        _want(wt3, 2, "Detection.classLabel")
+                        d["classLabel"] = _text(w)
                     elif f3 == 4:
-                        for f4, _, r in _fields(w):
+                        _want(wt3, 2, "Detection.boundingBox")
+                        for f4, wt4, r in _fields(w):
+                            if f4 not in (1, 2):
+                                continue
+                            _want(wt4, 2, "Rect.origin / Rect.size")
                             names = ("x", "y") if f4 == 1 else ("width", "height")
-                            for f5, _, val in _fields(r):
-                                d["boundingBox"][names[f5 - 1]] = val
+                            for f5, wt5, val in _fields(r):
+                                if f5 in (1, 2):
+                                    _want(wt5, 1, "Origin / Size double")
+                                    d["boundingBox"][names[f5 - 1]] = val
                 res["detections"].append(d)
         out.append(res)
     return out

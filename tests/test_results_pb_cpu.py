@@ -57,3 +57,27 @@ def test_results_wire_format_matches_google_protobuf(pkg):
     back = pkg.results_pb.decode_results(blob)
     assert back[0]["imageInfo"] == {"datasetId": "coco", "id": "139", "width": 640, "height": 426}
     assert len(back[0]["detections"]) == len(keep) and back[1]["detections"] == []
+
+
+def test_decoder_rejects_damaged_messages_with_valueerror(pkg):
+    rng = np.random.default_rng(0)
+    det = np.zeros((100, 6), np.float32)
+    det[:20, :4] = np.sort(rng.uniform(size=(20, 4)).astype(np.float32), axis=1)
+    det[:20, 4] = rng.integers(1, 81, 20)
+    det[:20, 5] = rng.uniform(0.71, 1.0, 20)
+    good = pkg.results_pb.encode_results([pkg.results_pb.result_from_detections("coco", 139, 640, 426, det)])
+    assert len(pkg.results_pb.decode_results(good)[0]["detections"]) == 20
+    ok = 0
+    for _ in range(3000):                               # truncations and byte flips: ValueError or a clean parse, nothing else
+        b = bytearray(good)
+        if rng.random() < 0.3:
+            b = b[:int(rng.integers(0, len(b)))]
+        else:
+            for _ in range(int(rng.integers(1, 4))):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        try:
+            pkg.results_pb.decode_results(bytes(b))
+            ok += 1
+        except ValueError:
+            pass
+    assert 0 < ok < 3000
