@@ -223,15 +223,23 @@ static int add_stage(mrcnn_ctx* ctx, Graph& g, int stage_index, const std::vecto
   return MRCNN_OK;
 }
 
-// Experiment knob (off by default): MRCNN_STAGE_SPLIT is a bit mask of the ResNet stages (bit 0 =
-// res2 ... bit 3 = res5) whose layers are launched per HALF batch -- all blocks of the stage for images [0, B/2), then
-// for images [B/2, B) -- so that one block's working set fits the L2 (res4 at batch 8: 170 MB -> 85 MB).  The launches
-// are derived from the full-batch ones by narrowing `n` and advancing the image-major NHWC pointers; tiles never span
-// images, so the results are bit-identical.
+// Experiment knob (off by default): MRCNN_STAGE_PARTS = "p2,p3,p4,p5" launches the layers of the
+// ResNet stages res2..res5 per 1/p-th of the batch -- all blocks of the stage for the first B/p images, then for the next
+// B/p, ... -- so that one block's working set fits the L2 (res4 at batch 8: 170 MB -> 85 MB with p = 2; res2: 670 MB ->
+// 84 MB with p = 8).  The launches are derived from the full-batch ones by narrowing `n` and advancing the image-major
+// NHWC pointers; tiles never span images, so the results are bit-identical.  A count that does not divide B is ignored.
 static int stage_split_parts(int stage_index, int B) {
-  const char* e = getenv("MRCNN_STAGE_SPLIT");
-  if (!e || !((atoi(e) >> stage_index) & 1) || B < 2 || (B & 1)) return 1;
-  return 2;
+  const char* e = getenv("MRCNN_STAGE_PARTS");
+  if (!e) return 1;
+  int parts = 1;
+  for (int i = 0; i <= stage_index && e; ++i) {
+    parts = atoi(e);
+    e = strchr(e, ',');
+    if (e) ++e;
+    else if (i < stage_index) parts = 1;      // list shorter than the stage index: not split
+  }
+  if (parts < 2 || parts > B || B % parts != 0) return 1;
+  return parts;
 }
 
 static std::vector<ConvLaunch> split_stage_by_images(const std::vector<ConvLaunch>& layers, int B, int parts) {

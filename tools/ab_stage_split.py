@@ -1,9 +1,9 @@
 #!/usr/bin/env python
-"""A/B of the half-batch stage split (MRCNN_STAGE_SPLIT, pipeline.cu: all blocks of a ResNet stage for images [0, B/2),
-then for [B/2, B), so that a block's working set fits the L2) against whole-batch launches in ONE process: one model per
-variant, the predict calls interleaved, CUDA-event timed; prints median / min ms per batch, images/s, the launch count per
-batch and whether the outputs are bit-identical (they must be: tiles never span images).
-  VARIANTS="0 4 6 14"   bit masks of the stages to split (bit 0 = res2 ... bit 3 = res5); 0 = off (the default path)"""
+"""A/B of the per-sub-batch stage launches (MRCNN_STAGE_PARTS, pipeline.cu: all blocks of a ResNet stage for the first
+B/p images, then for the next B/p, ..., so that a block's working set fits the L2) against whole-batch launches in ONE
+process: one model per variant, the predict calls interleaved, CUDA-event timed; prints median / min ms per batch,
+images/s, the launch count per batch and whether the outputs are bit-identical (they must be: tiles never span images).
+  VARIANTS="off 1,1,2,1 8,1,1,1 8,4,2,1"   parts per stage res2,res3,res4,res5; "off" = the default path"""
 import os
 import sys
 
@@ -17,17 +17,17 @@ import maskrcnn_b200 as m
 def main():
     batch = int(os.environ.get("BATCH", "8"))
     rounds = int(os.environ.get("ROUNDS", "12"))
-    variants = os.environ.get("VARIANTS", "0 4 6 14").split()
+    variants = os.environ.get("VARIANTS", "off 1,1,2,1 8,1,1,1 8,4,2,1").split()
     _, blobs = m.weights.synthetic_blobs(101)
     anchors = m.synth.generate_anchors(1024, 1024)
     img = torch.from_numpy(np.random.default_rng(0).integers(0, 256, (batch, 1024, 1024, 3), dtype=np.uint8)).cuda()
     stream = torch.cuda.Stream()
     models = []
     for v in variants:
-        if int(v):
-            os.environ["MRCNN_STAGE_SPLIT"] = v
+        if v != "off":
+            os.environ["MRCNN_STAGE_PARTS"] = v
         else:
-            os.environ.pop("MRCNN_STAGE_SPLIT", None)
+            os.environ.pop("MRCNN_STAGE_PARTS", None)
         cfg = m.MaskRCNNConfig()
         cfg.maxBatch = batch
         mod = m.MaskRCNN(cfg, blobs=blobs, anchors=anchors)
@@ -38,7 +38,7 @@ def main():
         n0 = mod.ctx.launch_count
         mod.prediction_batch(img, det, msk)
         models.append((v, mod, det, msk, mod.ctx.launch_count - n0))
-    os.environ.pop("MRCNN_STAGE_SPLIT", None)
+    os.environ.pop("MRCNN_STAGE_PARTS", None)
     torch.cuda.synchronize()
     times = {v: [] for v, *_ in models}
     for _ in range(rounds):
@@ -56,7 +56,7 @@ def main():
     same = all(np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1]) for o in outs[1:])
     for v, _, _, _, n in models:
         t = np.array(times[v])
-        print(f"split mask {v:>3s}: median {np.median(t):.3f} ms  min {t.min():.3f}  -> {batch / np.median(t) * 1e3:.1f} images/s, {n} launches per batch")
+        print(f"parts {v:>8s}: median {np.median(t):.3f} ms  min {t.min():.3f}  -> {batch / np.median(t) * 1e3:.1f} images/s, {n} launches per batch")
     print("outputs identical across variants:", same)
     for _, mod, *_ in models:
         mod.close()
