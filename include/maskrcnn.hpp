@@ -363,9 +363,9 @@ class PyramidROIAlignLayer : public CustomLayer {
       const std::int64_t w = f.shape.empty() ? 0 : f.shape[f.shape.size() - 1];
       const std::int64_t h = f.shape.size() < 2 ? 0 : f.shape[f.shape.size() - 2];
       need(h > 0 && w > 0 && f.count() % (h * w * batch) == 0, "feature maps must be (batch, C, H, W)");
-      const std::int64_t c = f.count() / (h * w * batch);
-      need(l == 0 || c == channels, "feature maps must have the same channel count");
-      channels = c;
+      const std::int64_t ch = f.count() / (h * w * batch);
+      need(l == 0 || ch == channels, "feature maps must have the same channel count");
+      channels = ch;
       maps[l] = f.data;
       hw[2 * l] = static_cast<std::int32_t>(h);
       hw[2 * l + 1] = static_cast<std::int32_t>(w);
