@@ -271,3 +271,32 @@ def test_literal_model_reproduces_the_committed_golden_fixtures():
         assert i == m["index"][k] and c == m["classes"][k] and sc == m["score"][k]
         np.testing.assert_array_equal(np.array(box), m["bbox"][k])
         np.testing.assert_array_equal(mask, m["mask_u8"][k])
+
+
+@pytest.mark.parametrize("size,pre,mx", [(1024, 6000, 1000), (512, 6000, 300)])
+def test_proposal_at_the_baseline_sizes_with_the_reference_index_range(orc, m, size, pre, mx):
+    """BASELINE.json configs A (261 888 anchors, 6000 -> 1000) and S (65 472 anchors, 6000 -> 300) at their exact sizes, the
+    literal model run with the reference's own 4x-too-long NMS index range (enough boxes survive, so it never traps)."""
+    anchors = m.synth.generate_anchors(size, size)
+    assert anchors.shape[0] == {1024: 261888, 512: 65472}[size]
+    probs, deltas = m.synth.rpn_outputs(anchors, 0, image_size=size)
+    rois, keep, cnt = orc.proposal(probs, deltas, anchors, pre_nms=pre, max_proposals=mx)
+    out, ri, order = lit.proposal_evaluate(probs, deltas, anchors, pre_nms=pre, max_proposals=mx, fix_q4=False)
+    assert cnt == mx == len(ri)
+    np.testing.assert_array_equal(out, rois)
+    np.testing.assert_array_equal(order[ri].astype(np.int32), keep)
+    # and the layers behind it on those rois: level rule + pooled values of a few rois on full-size maps, DetectionLayer
+    maps = m.synth.feature_maps(0, size, size, channels=4)
+    pick = rois[:: mx // 25]
+    pooled, lv = orc.pyramid_roialign(pick, maps, 7, size, size)
+    items = lit.rois_to_input_items(pick, 224.0, float(size), float(size))
+    np.testing.assert_array_equal(np.array([c[0] + 2 for _, c in items], np.int32), lv)
+    for i, (_, (mi, box)) in enumerate(items):
+        np.testing.assert_array_equal(lit.crop_and_resize_bilinear(maps[mi], box, 7), pooled[i])
+    pr, bb = m.synth.classifier_outputs(mx, 0)
+    cls = orc.classifier_select(pr, bb)
+    det, dkeep, dcnt = orc.detection(rois, cls)
+    dout, didx = lit.detection_evaluate(rois, cls)
+    assert dcnt == len(didx) and dcnt > 0
+    np.testing.assert_array_equal(dout, det)
+    np.testing.assert_array_equal(np.array(didx, np.int32), dkeep[:dcnt])
