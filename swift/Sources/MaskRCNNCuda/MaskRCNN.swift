@@ -68,6 +68,15 @@ public final class MaskRCNN {
             return mrcnn_create(&cfg, &ctx)
         }
         if status != 0 { throw MaskRCNNError(status: status, description: String(cString: mrcnn_last_error(nil))) }
+        if configuration.anchorsURL == nil {
+            // the reference's own TODO (MaskRCNNConfig.swift:14): anchors generated for the input size instead of anchors.bin
+            let n = mrcnn_anchor_count(cfg.image_h, cfg.image_w)
+            if n < 0 { throw MaskRCNNError(status: Int32(n), description: "mrcnn_anchor_count: bad image size") }
+            var anchors = [Float](repeating: 0, count: Int(n) * 4)
+            var st = mrcnn_generate_anchors(cfg.image_h, cfg.image_w, &anchors, n)
+            if st == 0 { st = mrcnn_set_anchors(ctx, anchors, n) }
+            if st != 0 { throw MaskRCNNError(status: st, description: String(cString: mrcnn_last_error(ctx))) }
+        }
     }
 
     deinit { mrcnn_destroy(ctx) }
