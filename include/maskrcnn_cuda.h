@@ -318,10 +318,6 @@ MRCNN_API int mrcnn_conv2d_nhwc_f16(mrcnn_ctx* ctx, const void* x, int n, int h,
 /* Debug: per-CTA event trace (clock64 stamps of the producer / MMA / epilogue roles) of the next
  * mrcnn_conv2d_nhwc_f16 calls; device buffer of 148 * 3 * (2*340 + 2) u64, NULL = off (tools/trace_conv.py). */
 MRCNN_API int mrcnn_debug_conv_trace(void* device_buffer);
-/* Debug: per-CTA stall statistics (clock64 totals per role) of the next chained ResNet-stage launches (conv_chain.cuh):
- * after skipping `skip` chain launches, up to 8 launches write 148 x 16 u64 each into device_buffer; NULL = off
- * (tools/chain_stats.py). */
-MRCNN_API int mrcnn_debug_chain_stats(void* device_buffer, int skip);
 /* Backbone + FPN + RPN only (stage-level parity hook; device pointers only):
  *   rgb [batch,H,W,3] u8 -> fmaps_out[l] [batch,H_l,W_l,256] f16 NHWC (P2..P5),
  *   probs_out [batch,N,2] f32, deltas_out [batch,N,4] f32. */

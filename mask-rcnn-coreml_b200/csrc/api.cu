@@ -141,6 +141,7 @@ void mrcnn_destroy(mrcnn_ctx* ctx) {
   cudaFree(ctx->d_fbox); cudaFree(ctx->d_fcls); cudaFree(ctx->d_fscore);
   cudaFree(ctx->d_fidx); cudaFree(ctx->d_fcount); cudaFree(ctx->d_dmask);
   cudaFree(ctx->d_roi_level);
+  roialign_release(ctx);
   cudaFree(ctx->d_gather_send); cudaFree(ctx->d_gather_recv);
   for (auto& pr : ctx->prof_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);

@@ -55,6 +55,7 @@ struct mrcnn_ctx {
   // ---- roialign workspace ----
   int roi_cap = 0;            // batch*R capacity
   int32_t* d_roi_level = nullptr;
+  void* roi_tma = nullptr;    // roialign.cu: tensor maps of the staged kernel (RoiTmaCache)
 
   // ---- dense model (backbone / heads) ----
   DenseModel* dense = nullptr;
@@ -221,6 +222,7 @@ int roialign_chw_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int roi_str
 int roialign_nhwc_f16_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int roi_stride, int64_t R,
                           const __half* const d_fmaps[4], const int32_t hw[8], int64_t C, int P,
                           __half* d_out, int32_t* d_level_out);
+void roialign_release(mrcnn_ctx* ctx);
 int classifier_select_run(mrcnn_ctx* ctx, int batch, int64_t R, int ncls, const float* d_probs,
                           const float* d_bbox, float* d_out);
 int detections_decode_run(mrcnn_ctx* ctx, int batch, int D, int S, const float* d_det, const float* d_masks,

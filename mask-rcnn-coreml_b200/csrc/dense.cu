@@ -1,6 +1,5 @@
 // dense.cu -- host side of the tcgen05 implicit-GEMM convolution (conv_gemm.cuh):
 // TMA tensor-map construction, tile-shape selection and launch.
-#define CONV_CHAIN_KERNEL
 #include "dense.h"
 #include <string.h>
 #include <stdlib.h>
@@ -257,182 +256,6 @@ int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan) {
   return MRCNN_OK;
 }
 
-// ------------------------------------------------------------------------------
-// Chains (conv_chain.cuh)
-// ------------------------------------------------------------------------------
-int chain_plan_build(mrcnn_ctx* ctx, const std::vector<ConvLaunch>& layers, ChainPlan* plan) {
-  const int nl = (int)layers.size();
-  MRCNN_REQUIRE(ctx, nl >= 1 && nl <= CH_MAX_LAYERS, "chain: needs 1..CH_MAX_LAYERS layers");
-  ChainParams& cp = plan->params;
-  memset(&cp, 0, sizeof(cp));
-  std::vector<CUtensorMap> maps((size_t)nl * 4);
-  std::map<const void*, int> writer;       // buffer -> chain layer that wrote it last
-  uint32_t items = 0;
-  double flops = 0;
-  long max_tiles_m = 0;
-  std::vector<uint32_t> layer_pm(nl);
-  std::vector<long> layer_tiles_m(nl);
-  const int n_img = layers[0].n;
-  for (int l = 0; l < nl; ++l) {
-    ConvLaunch L = layers[l];
-    MRCNN_REQUIRE(ctx, L.n == n_img, "chain: all layers must have the same batch");
-    MRCNN_REQUIRE(ctx, L.cout % 64 == 0, "chain: cout must be a multiple of 64");
-    MRCNN_REQUIRE(ctx, L.bias != nullptr, "chain: layers need a bias vector");
-    L.ctas = 2;
-    L.no_vgroup = 1;
-    L.bn = L.cout >= 256 ? 256 : L.cout;   // 64, 128 or 256: always divides cout here
-    MRCNN_REQUIRE(ctx, L.cout % L.bn == 0, "chain: cout must be a multiple of the N tile");
-    ConvPlan cpl;
-    int rc = conv_plan_build(ctx, L, &cpl);
-    if (rc) return rc;
-    const ConvGemmParams& p = cpl.p;
-    MRCNN_REQUIRE(ctx, p.ctas == 2 && p.tma_out && !p.split_out && !p.maskdot && !p.deconv && !p.out_f32,
-                  "chain: layer needs the CTA-pair kernel with the staged TMA-store epilogue");
-    MRCNN_REQUIRE(ctx, p.res_mode == 0 || (p.res_mode == 1 && p.tma_res), "chain: only TMA-fetched same-resolution residuals");
-    MRCNN_REQUIRE(ctx, p.ntaps <= CH_MAX_TAPS && p.cin / CG_BK <= 65535, "chain: too many taps");
-    MRCNN_REQUIRE(ctx, p.tiles_x * p.tiles_y <= 65535 && p.tiles_n <= 65535, "chain: too many tiles per image");
-    ChainLayer& C = cp.L[l];
-    const long tiles_m = (long)p.n_img * p.tiles_x * p.tiles_y;
-    layer_pm[l] = (uint32_t)((tiles_m + 1) / 2);           // pair tiles (256 pixels) of this layer
-    layer_tiles_m[l] = tiles_m;
-    C.tiles_x = (uint16_t)p.tiles_x; C.tiles_y = (uint16_t)p.tiles_y; C.tiles_n = (uint16_t)p.tiles_n;
-    C.tiles_per_img = (uint16_t)(p.tiles_x * p.tiles_y);
-    C.cout = (uint16_t)p.cout; C.bn = (uint16_t)cpl.bn; C.cin_chunks = (uint16_t)(p.cin / CG_BK);
-    C.ntaps = (uint8_t)p.ntaps; C.stride = (uint8_t)p.stride; C.tw = (uint8_t)p.tw; C.th = (uint8_t)p.th;
-    C.relu = (uint8_t)(p.relu ? 1 : 0); C.res = (uint8_t)(p.res_mode ? 1 : 0);
-    for (int t = 0; t < p.ntaps; ++t) { C.tap_dx[t] = p.tap_dx[t]; C.tap_dy[t] = p.tap_dy[t]; }
-    C.bias = p.bias;
-    // dependencies at tile granularity: the producing layer must have the same tile grid, and this layer must read
-    // its input tile-aligned (stride 1; a 1x1 convolution reads the same tile, a 3x3 one the tile neighbourhood)
-    auto dep = [&](const void* buf, int16_t* idx, uint16_t* need, bool allow_nbhd, uint8_t* nbhd) -> bool {
-      *idx = -1; *need = 0;
-      if (nbhd) *nbhd = 0;
-      auto it = writer.find(buf);
-      if (it == writer.end()) return true;
-      const ChainLayer& W = cp.L[it->second];
-      if (W.tiles_x != C.tiles_x || W.tiles_y != C.tiles_y || W.tw != C.tw || W.th != C.th || p.stride != 1) return false;
-      int reach = 0;
-      for (int t = 0; t < p.ntaps; ++t) {
-        reach = std::max(reach, std::abs((int)p.tap_dx[t]));
-        reach = std::max(reach, std::abs((int)p.tap_dy[t]));
-      }
-      if (!allow_nbhd) reach = 0;
-      if (reach > 0) {
-        if (!nbhd || reach > std::min((int)C.tw, (int)C.th)) return false;
-        *nbhd = 1;
-      }
-      *idx = (int16_t)it->second;
-      *need = (uint16_t)W.tiles_n;
-      return true;
-    };
-    MRCNN_REQUIRE(ctx, dep(L.x, &C.dep_a, &C.need_a, true, &C.nbhd_a), "chain: input dependency is not tile aligned");
-    MRCNN_REQUIRE(ctx, dep(L.residual, &C.dep_r, &C.need_r, false, nullptr), "chain: residual dependency is not tile aligned");
-    max_tiles_m = std::max(max_tiles_m, tiles_m + 1);
-    writer[L.out] = l;
-    maps[4 * l + 0] = cpl.tmA; maps[4 * l + 1] = cpl.tmB; maps[4 * l + 2] = cpl.tmC; maps[4 * l + 3] = cpl.tmR;
-    flops += cpl.flops;
-  }
-  // ---- the work list.  Two halves of the batch run `lag` layers apart and are zipped (see ChainSeg): each half is
-  // dependency-closed (whole images), so every dependency still points backwards in the list.
-  {
-    const char* e = getenv("MRCNN_CHAIN_LAG");
-    int lag = e ? atoi(e) : 0;      // measured on B200: the lagged order stalls more than it overlaps; kept for experiments
-    const int img_a = n_img / 2;                                   // images of the first half
-    bool split = lag > 0 && n_img >= 2;
-    for (int l = 0; l < nl && split; ++l)
-      if (((long)cp.L[l].tiles_per_img * img_a) % 2 != 0) split = false;     // a CTA pair must not straddle the halves
-    int ns = 0;
-    auto push = [&](int lx, uint32_t x0, uint32_t nx, int ly, uint32_t y0, uint32_t ny) -> bool {
-      if (nx == 0 && ny == 0) return true;
-      if (ns >= CH_MAX_SEGS) return false;
-      ChainSeg& G = cp.S[ns++];
-      if (nx == 0) { lx = ly; x0 = y0; nx = ny; ly = -1; y0 = 0; ny = 0; }
-      if (ny == 0) ly = -1;
-      items += nx + ny;
-      G.item_end = items; G.lx = (int16_t)lx; G.ly = (int16_t)ly; G.x0 = x0; G.y0 = y0; G.nx = nx; G.ny = ny;
-      return true;
-    };
-    bool ok = true;
-    if (!split) {
-      for (int l = 0; l < nl && ok; ++l) ok = push(l, 0, layer_pm[l] * cp.L[l].tiles_n, -1, 0, 0);
-    } else {
-      for (int t = 0; t < nl + lag && ok; ++t) {
-        const int la = t < nl ? t : -1, lb = t - lag >= 0 ? t - lag : -1;
-        uint32_t xa0 = 0, na = 0, yb0 = 0, nb = 0;
-        if (la >= 0) { const uint32_t pa = (uint32_t)((long)cp.L[la].tiles_per_img * img_a / 2); na = pa * cp.L[la].tiles_n; xa0 = 0; }
-        if (lb >= 0) {
-          const uint32_t pa = (uint32_t)((long)cp.L[lb].tiles_per_img * img_a / 2);
-          yb0 = pa * cp.L[lb].tiles_n; nb = (layer_pm[lb] - pa) * cp.L[lb].tiles_n;
-        }
-        ok = push(la, xa0, na, lb, yb0, nb);
-      }
-    }
-    MRCNN_REQUIRE(ctx, ok, "chain: too many segments");
-    cp.n_segs = ns;
-  }
-  cp.n_layers = nl; cp.n_img = n_img; cp.total_items = items;
-  cp.flag_stride = (int)((max_tiles_m + 15) / 16 * 16);
-  plan->flops = flops;
-  plan->done_bytes = sizeof(uint32_t) * (size_t)nl * cp.flag_stride;
-  MRCNN_CUDA_TRY(ctx, cudaMalloc(&plan->d_maps, sizeof(CUtensorMap) * maps.size()));
-  MRCNN_CUDA_TRY(ctx, cudaMalloc(&plan->d_done, plan->done_bytes));
-  MRCNN_CUDA_TRY(ctx, cudaMemcpyAsync(plan->d_maps, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice, ctx->stream));
-  MRCNN_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));    // `maps` is a local
-  cp.maps = plan->d_maps; cp.done = plan->d_done;
-  // every CTA pair must be resident at the same time (items wait for items of other pairs): ask the driver
-  static bool attr_done[64] = {false};
-  const int dv = ctx->device & 63;
-  if (!attr_done[dv]) {
-    MRCNN_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES));
-    attr_done[dv] = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(ctx->sm_count / 2 * 2); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = CH_SMEM_BYTES;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  int max_clusters = 0;
-  MRCNN_CUDA_TRY(ctx, cudaOccupancyMaxActiveClusters(&max_clusters, conv_chain_kernel, &cfg));
-  MRCNN_REQUIRE(ctx, max_clusters >= 1, "chain: no CTA pair of the chain kernel fits on this device");
-  long pairs = ctx->sm_count / 2;
-  if (pairs > max_clusters) pairs = max_clusters;
-  if (pairs > (long)items) pairs = (long)items;
-  plan->grid = (int)pairs * 2;
-  return MRCNN_OK;
-}
-
-static unsigned long long* g_chain_stats = nullptr;   // set by mrcnn_debug_chain_stats
-static int g_chain_stats_launches = 0, g_chain_stats_skip = 0;
-
-int chain_plan_run(mrcnn_ctx* ctx, const ChainPlan& plan) {
-  MRCNN_CUDA_TRY(ctx, cudaMemsetAsync(plan.d_done, 0, plan.done_bytes, ctx->stream));
-  ChainParams params_dbg;
-  const ChainParams* params = &plan.params;
-  if (g_chain_stats) {             // debug: launch number k (after `skip` launches) writes its per-CTA stall clocks to slot k
-    if (g_chain_stats_skip > 0) --g_chain_stats_skip;
-    else if (g_chain_stats_launches < 8) {
-      params_dbg = plan.params;
-      params_dbg.stats = g_chain_stats + (size_t)g_chain_stats_launches * 148 * CH_NSTAT;
-      params = &params_dbg;
-      ++g_chain_stats_launches;
-    }
-  }
-  ProfScope ps(ctx, PROF_CONV_GEMM, plan.flops);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(plan.grid); cfg.blockDim = dim3(CH_THREADS);
-  cfg.dynamicSmemBytes = CH_SMEM_BYTES; cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 2;
-  MRCNN_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, conv_chain_kernel, *params));
-  MRCNN_LAUNCH_CHECK(ctx);
-  return MRCNN_OK;
-}
-
 static unsigned long long* g_trace_buf = nullptr;   // set by mrcnn_debug_conv_trace; picked up by the conv2d hook only
 
 extern "C" {
@@ -440,13 +263,6 @@ extern "C" {
 // Debug: device buffer of gridDim * 3 * (2 * 340 + 2) u64 that the NEXT mrcnn_conv2d_nhwc_f16 calls write their per-CTA event
 // traces into (tools/trace_conv.py); NULL switches tracing off.  Not part of the reference-facing surface.
 MRCNN_API int mrcnn_debug_conv_trace(void* device_buffer) { g_trace_buf = (unsigned long long*)device_buffer; return MRCNN_OK; }
-
-// Debug: the next chain launches (after skipping `skip` of them) write per-CTA stall statistics (CH_STAT_*, clock64 totals)
-// into device_buffer: up to 8 launches x 148 CTAs x CH_NSTAT u64 (tools/chain_stats.py).  NULL switches it off.
-MRCNN_API int mrcnn_debug_chain_stats(void* device_buffer, int skip) {
-  g_chain_stats = (unsigned long long*)device_buffer; g_chain_stats_launches = 0; g_chain_stats_skip = skip;
-  return MRCNN_OK;
-}
 
 // Test / bench hook: one NHWC fp16 convolution through the tcgen05 kernel.
 //   x [n,h,w,cin] f16, wgt [cout,kh,kw,cin] f16, bias [cout] f32 or NULL,

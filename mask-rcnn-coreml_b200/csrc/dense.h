@@ -4,7 +4,6 @@
 #include "common.cuh"
 #include <string.h>
 #include "conv_gemm.cuh"
-#include "conv_chain.cuh"
 
 // One convolution (or GEMM) as the caller sees it.  Activations are NHWC fp16.
 struct ConvLaunch {
@@ -32,7 +31,7 @@ struct ConvLaunch {
   unsigned long long* trace = nullptr;   // debug event trace buffer (device), see cg::trace_ev
   int ctas = 0;                  // 0 -> auto (env MRCNN_CONV_CTAS overrides), 1 = one CTA per tile, 2 = CTA pairs (cta_group::2)
   int no_tma_epilogue = 0;       // force the direct-store epilogue (tests)
-  int no_vgroup = 0;             // one A tile per tap even for 3x3 convolutions (the chain kernel has no patch ring)
+  int no_vgroup = 0;             // one A tile per tap even for 3x3 convolutions
   // mask-head tail fused into the deconv epilogue (needs deconv = 1, deconv_c == bn == 256): out = f32 [n, 2h, 2w]
   int maskdot = 0;
   const int32_t* md_valid = nullptr;
@@ -54,25 +53,6 @@ struct ConvPlan {
 
 int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan);
 int conv_plan_run(mrcnn_ctx* ctx, const ConvPlan& plan);
-
-// A sequence of convolutions as one persistent launch with image-granular dataflow between the layers
-// (conv_chain.cuh).  Dependencies are derived from the buffers: a layer depends on the chain layers that wrote its
-// input and its residual.
-struct ChainPlan {
-  ChainParams params;
-  CUtensorMap* d_maps = nullptr;     // [n_layers][4]
-  uint32_t* d_done = nullptr;        // [n_layers][flag_stride]
-  size_t done_bytes = 0;
-  int grid = 0;
-  double flops = 0;
-  ChainPlan() { memset(&params, 0, sizeof(params)); }
-  ~ChainPlan() { cudaFree(d_maps); cudaFree(d_done); }
-  ChainPlan(const ChainPlan&) = delete;
-  ChainPlan& operator=(const ChainPlan&) = delete;
-};
-// MRCNN_EINVAL (with a message) when a layer cannot run in a chain; the caller then launches the layers one by one.
-int chain_plan_build(mrcnn_ctx* ctx, const std::vector<ConvLaunch>& layers, ChainPlan* plan);
-int chain_plan_run(mrcnn_ctx* ctx, const ChainPlan& plan);
 
 int dense_load_weights(mrcnn_ctx* ctx, int which, const void* blob, size_t bytes);
 void dense_destroy(mrcnn_ctx* ctx);

@@ -190,80 +190,14 @@ static int add_conv(mrcnn_ctx* ctx, Graph& g, int which, const ConvArgs& a) {
   return add_conv_launch(ctx, g, L, a.wname);
 }
 
-// A ResNet stage: one persistent chain launch (conv_chain.cuh) when every layer qualifies, else layer by layer.
-// MRCNN_CHAIN=0 switches chains off; MRCNN_CHAIN_STAGES is a bit mask of the stages (bit 0 = res2) that may chain.
-static int add_stage(mrcnn_ctx* ctx, Graph& g, int stage_index, const std::vector<ConvLaunch>& layers) {
-  const char* e = getenv("MRCNN_CHAIN");
-  const char* em = getenv("MRCNN_CHAIN_STAGES");
-  const bool chain_on = e ? atoi(e) != 0 : false;    // experimental: off unless MRCNN_CHAIN=1
-  const int stage_mask = em ? atoi(em) : 0xF;
-  if (chain_on && ((stage_mask >> stage_index) & 1) && layers.size() >= 2) {
-    const char* el = getenv("MRCNN_CHAIN_MAXLEN");        // experiment knob: split a stage into sub-chains of at most N layers
-    const size_t maxlen = el && atoi(el) > 0 ? (size_t)atoi(el) : (size_t)CH_MAX_LAYERS;
-    std::vector<std::shared_ptr<ChainPlan>> plans;
-    int rc = MRCNN_OK;
-    const std::string saved = ctx->err;
-    for (size_t i0 = 0; i0 < layers.size() && rc == MRCNN_OK; i0 += maxlen) {
-      const size_t i1 = std::min(layers.size(), i0 + maxlen);
-      auto plan = std::make_shared<ChainPlan>();
-      rc = chain_plan_build(ctx, std::vector<ConvLaunch>(layers.begin() + i0, layers.begin() + i1), plan.get());
-      plans.push_back(plan);
-    }
-    if (rc == MRCNN_OK) {
-      for (auto& plan : plans) g.push_back([plan](mrcnn_ctx* c) { return chain_plan_run(c, *plan); });
-      return MRCNN_OK;
-    }
-    if (rc != MRCNN_EINVAL) return rc;
-    ctx->err = saved;                      // not chainable (e.g. tiny maps): launch the layers one by one
-  }
+// A ResNet stage: its layers, launched one by one.  (Two experiments that regrouped these launches lost on B200 and were
+// removed: one persistent dataflow launch per stage, and per-sub-batch launches to keep a block in L2 -- DESIGN.md 8.)
+static int add_stage(mrcnn_ctx* ctx, Graph& g, const std::vector<ConvLaunch>& layers) {
   for (const ConvLaunch& L : layers) {
     int rc = add_conv_launch(ctx, g, L, "resnet stage layer");
     if (rc) return rc;
   }
   return MRCNN_OK;
-}
-
-// Experiment knob (off by default): MRCNN_STAGE_PARTS = "p2,p3,p4,p5" launches the layers of the
-// ResNet stages res2..res5 per 1/p-th of the batch -- all blocks of the stage for the first B/p images, then for the next
-// B/p, ... -- so that one block's working set fits the L2 (res4 at batch 8: 170 MB -> 85 MB with p = 2; res2: 670 MB ->
-// 84 MB with p = 8).  The launches are derived from the full-batch ones by narrowing `n` and advancing the image-major
-// NHWC pointers; tiles never span images, so the results are bit-identical.  A count that does not divide B is ignored.
-static int stage_split_parts(int stage_index, int B) {
-  const char* e = getenv("MRCNN_STAGE_PARTS");
-  if (!e) return 1;
-  int parts = 1;
-  for (int i = 0; i <= stage_index && e; ++i) {
-    parts = atoi(e);
-    e = strchr(e, ',');
-    if (e) ++e;
-    else if (i < stage_index) parts = 1;      // list shorter than the stage index: not split
-  }
-  if (parts < 2 || parts > B || B % parts != 0) return 1;
-  return parts;
-}
-
-static std::vector<ConvLaunch> split_stage_by_images(const std::vector<ConvLaunch>& layers, int B, int parts) {
-  std::vector<ConvLaunch> out;
-  const int nb = B / parts;
-  for (int k = 0; k < parts; ++k) {
-    for (const ConvLaunch& L0 : layers) {
-      ConvLaunch L = L0;
-      const size_t ld_in = (size_t)(L0.ld_in ? L0.ld_in : L0.cin);
-      const size_t ho = (size_t)(L0.h_out ? L0.h_out : (L0.h_in + 2 * L0.pad - L0.kh) / L0.stride + 1);
-      const size_t wo = (size_t)(L0.w_out ? L0.w_out : (L0.w_in + 2 * L0.pad - L0.kw) / L0.stride + 1);
-      const size_t ldc = (size_t)(L0.ldc ? L0.ldc : (L0.cout + 7) / 8 * 8);
-      const size_t img0 = (size_t)k * nb;
-      L.n = nb;
-      L.x = L0.x + img0 * L0.h_in * L0.w_in * ld_in;
-      L.out = (void*)((__half*)L0.out + img0 * ho * wo * ldc);
-      if (L0.residual) {
-        const size_t rh = (size_t)(L0.res_h ? L0.res_h : (int)ho), rw = (size_t)(L0.res_w ? L0.res_w : (int)wo);
-        L.residual = L0.residual + img0 * rh * rw * (size_t)(L0.res_ld ? L0.res_ld : (int)ldc);
-      }
-      out.push_back(L);
-    }
-  }
-  return out;
 }
 
 #define TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
@@ -286,17 +220,12 @@ static int build_backbone(mrcnn_ctx* ctx, int B, std::shared_ptr<Graph>* out_gra
   const int H1 = H / 2, W1 = W / 2;                         // conv1 output
   const int H2 = H / 4, W2 = W / 4;                         // C2
   auto elems = [&](int h, int w, int c) { return (size_t)MB * h * w * c; };
-  __half *s2d, *a, *b, *pool, *t1, *t1b, *t2, *sc, *c2, *c3, *c4, *c5;
+  __half *s2d, *a, *b, *pool, *t1, *t2, *sc, *c2, *c3, *c4, *c5;
   TRY(get_buf(ctx, "s2d", elems(Hs, Ws, 16) * 2, (void**)&s2d));
   TRY(get_buf(ctx, "actA", elems(H1, W1, 64) * 2, (void**)&a));
   TRY(get_buf(ctx, "actB", elems(H2, W2, 256) * 2, (void**)&b));
-  // the max-pool output has its own buffer: inside a chained stage a ping-pong buffer may only ever be reused with the
-  // geometry of that stage (the per-image dependencies do not order accesses to differently laid out images)
   TRY(get_buf(ctx, "pool", elems(H2, W2, 64) * 2, (void**)&pool));
   TRY(get_buf(ctx, "t1", elems(H2, W2, 64) * 2, (void**)&t1));
-  // second copy of the 2a output: inside a chained stage block k+1 may write its 2a tile while a neighbouring tile of
-  // block k's 3x3 convolution still reads the halo; alternating the buffer per block makes that safe (conv_chain.cuh)
-  TRY(get_buf(ctx, "t1b", elems(H2, W2, 64) * 2, (void**)&t1b));
   TRY(get_buf(ctx, "t2", elems(H2, W2, 64) * 2, (void**)&t2));
   TRY(get_buf(ctx, "sc", elems(H2, W2, 256) * 2, (void**)&sc));
   TRY(get_buf(ctx, "c2", elems(H2, W2, 256) * 2, (void**)&c2));
@@ -365,10 +294,10 @@ static int build_backbone(mrcnn_ctx* ctx, int B, std::shared_ptr<Graph>* out_gra
       snprintf(n2c, 64, "res%d.%d.2c", s + 2, i); snprintf(n1, 64, "res%d.%d.1", s + 2, i);
       __half* y = (i == nb[s] - 1) ? stage_out[s] : pp[cur ^ 1];
       ConvArgs A;
-      A.wname = n2a; A.x = x; A.n = B; A.h = h; A.w = w; A.cin = cin; A.cout = f; A.k = 1; A.stride = stride; A.relu = 1; A.out = (i & 1) ? t1b : t1;
+      A.wname = n2a; A.x = x; A.n = B; A.h = h; A.w = w; A.cin = cin; A.cout = f; A.k = 1; A.stride = stride; A.relu = 1; A.out = t1;
       TRY(stage_conv(A));
       ConvArgs Bc;
-      Bc.wname = n2b; Bc.x = (i & 1) ? t1b : t1; Bc.n = B; Bc.h = ho; Bc.w = wo; Bc.cin = f; Bc.cout = f; Bc.k = 3; Bc.pad = 1; Bc.relu = 1; Bc.out = t2;
+      Bc.wname = n2b; Bc.x = t1; Bc.n = B; Bc.h = ho; Bc.w = wo; Bc.cin = f; Bc.cout = f; Bc.k = 3; Bc.pad = 1; Bc.relu = 1; Bc.out = t2;
       TRY(stage_conv(Bc));
       const __half* res = x;
       if (i == 0) {
@@ -384,9 +313,7 @@ static int build_backbone(mrcnn_ctx* ctx, int B, std::shared_ptr<Graph>* out_gra
       if (y == pp[cur ^ 1]) cur ^= 1;
       x = y; h = ho; w = wo; cin = 4 * f;
     }
-    const int parts = stage_split_parts(s, B);
-    if (parts > 1) stage_layers = split_stage_by_images(stage_layers, B, parts);
-    TRY(add_stage(ctx, *g, s, stage_layers));
+    TRY(add_stage(ctx, *g, stage_layers));
   }
   // ---- FPN
   const int lh[5] = {H2, H2 / 2, H2 / 4, H2 / 8, H2 / 16}, lw[5] = {W2, W2 / 2, W2 / 4, W2 / 8, W2 / 16};
@@ -666,17 +593,22 @@ static int predict_device(mrcnn_ctx* ctx, int B, const uint8_t* d_rgb, float* d_
   const int R = cfg.max_proposals, D = cfg.max_detections, P7 = cfg.pool_size_classifier, P14 = cfg.pool_size_mask;
   // build (or fetch) every graph first: building may reallocate shared buffers
   std::shared_ptr<Graph> gb, gc, gm;
+  float *rois = nullptr, *cls6 = nullptr;
+  const int MB = cfg.max_batch > B ? cfg.max_batch : B;
   for (int pass = 0; pass < 2; ++pass) {
+    // every buffer of the call is reserved inside this loop: a buffer that grows drops the cached graphs (get_buf),
+    // so the check at the end of the pass must come after the last reservation
+    TRY(get_buf(ctx, "rois", (size_t)MB * R * 4 * 4, (void**)&rois));
+    TRY(get_buf(ctx, "cls6", (size_t)MB * R * 6 * 4, (void**)&cls6));
     TRY(backbone_graph(ctx, B, &gb));
     TRY(cls_graph(ctx, (int64_t)B * R, &gc));
     TRY(mask_graph(ctx, (int64_t)B * D, &gm));
-    if (m->g_backbone.count(B) && m->g_cls.count((int64_t)B * R) && m->g_mask.count((int64_t)B * D)) break;
+    if (m->g_backbone.count(B) && m->g_cls.count((int64_t)B * R) && m->g_mask.count((int64_t)B * D) &&
+        m->mask_last.count((int64_t)B * D)) break;
   }
+  MRCNN_REQUIRE(ctx, m->g_backbone.count(B) && m->g_cls.count((int64_t)B * R) && m->g_mask.count((int64_t)B * D) &&
+                m->mask_last.count((int64_t)B * D), "predict: internal error, graphs invalidated while building");
   MRCNN_REQUIRE(ctx, ctx->d_anchors && ctx->num_anchors == m->n_anchors, "predict: anchors not loaded or anchor count does not match the image size");
-  float *rois, *cls6;
-  const int MB = cfg.max_batch > B ? cfg.max_batch : B;
-  TRY(get_buf(ctx, "rois", (size_t)MB * R * 4 * 4, (void**)&rois));
-  TRY(get_buf(ctx, "cls6", (size_t)MB * R * 6 * 4, (void**)&cls6));
   m->rgb = d_rgb;     // consumed by the pre-processing closure
   m->n_ev = 0;
   stage_mark(ctx, "start");

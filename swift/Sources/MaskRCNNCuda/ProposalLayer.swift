@@ -18,15 +18,30 @@ import CMaskRCNNCuda
         if let v = parameters["maxProposals"] as? Int { cfg.max_proposals = Int32(v); maxProposals = v } // :85-87
         if let v = parameters["nmsIOUThreshold"] as? Double { cfg.proposal_nms_iou = Float(v) }          // :88-90
         if let n = parameters["bboxStdDev_count"] as? Int, n == 4 {                                       // :70-80
-            withUnsafeMutablePointer(to: &cfg.bbox_std) { p in
-                p.withMemoryRebound(to: Float.self, capacity: 4) { q in
-                    for i in 0..<4 { if let v = parameters["bboxStdDev_\(i)"] as? Double { q[i] = Float(v) } }
-                }
-            }
+            // all or none, like the reference: the defaults stay unless every one of the `count` items is a Double
+            var v = [Float]()
+            for i in 0..<n { if let d = parameters["bboxStdDev_\(i)"] as? Double { v.append(Float(d)) } }
+            if v.count == n { cfg.bbox_std = (v[0], v[1], v[2], v[3]) }
         }
-        let anchors = MaskRCNNConfig.defaultConfig.anchorsURL!.path                                       // :68
-        let status = anchors.withCString { p -> Int32 in cfg.anchors_path = p; return mrcnn_create(&cfg, &ctx) }
+        // anchors.bin when the configuration names one (:68), else generated for the input size (the reference's own
+        // TODO, MaskRCNNConfig.swift:14) -- as MaskRCNN.swift does
+        let anchorsPath = MaskRCNNConfig.defaultConfig.anchorsURL?.path
+        var status: Int32
+        if let path = anchorsPath {
+            status = path.withCString { p -> Int32 in cfg.anchors_path = p; return mrcnn_create(&cfg, &ctx) }
+        } else {
+            cfg.anchors_path = nil
+            status = mrcnn_create(&cfg, &ctx)
+        }
         if status != 0 { throw MaskRCNNError(status: status, description: String(cString: mrcnn_last_error(nil))) }
+        if anchorsPath == nil {
+            let n = mrcnn_anchor_count(cfg.image_h, cfg.image_w)
+            if n < 0 { throw MaskRCNNError(status: Int32(n), description: "mrcnn_anchor_count: bad image size") }
+            var anchors = [Float](repeating: 0, count: Int(n) * 4)
+            status = mrcnn_generate_anchors(cfg.image_h, cfg.image_w, &anchors, n)
+            if status == 0 { status = mrcnn_set_anchors(ctx, anchors, n) }
+            if status != 0 { throw MaskRCNNError(status: status, description: String(cString: mrcnn_last_error(ctx))) }
+        }
     }
 
     deinit { mrcnn_destroy(ctx) }

@@ -71,8 +71,8 @@ def test_fullsize_proposal_nms_idempotent(pkg, full, orc):
 def test_config_s_resnet50_512_predict_equals_stagewise_chain(pkg, orc, monkeypatch):
     """BASELINE.json configs[2] at its exact size (ResNet50, 512x512, N = 65,472 anchors, 6000 -> 300 proposals):
     mrcnn_predict == backbone_eval -> oracle ProposalLayer -> oracle PyramidROIAlign -> classifier_eval ->
-    oracle DetectionLayer -> oracle PyramidROIAlign(14) -> mask_eval, bit for bit; the same with the ResNet stages
-    chained into persistent launches (conv_chain.cuh).  Level rule with the configured image size (quirk Q15)."""
+    oracle DetectionLayer -> oracle PyramidROIAlign(14) -> mask_eval, bit for bit.  Level rule with the configured
+    image size (quirk Q15)."""
     import ctypes as C
     import torch
     size, R = 512, 300
@@ -82,59 +82,29 @@ def test_config_s_resnet50_512_predict_equals_stagewise_chain(pkg, orc, monkeypa
     rng = np.random.default_rng(20262)
     img = rng.integers(0, 256, (2, size // 8, size // 8, 3)).astype(np.uint8).repeat(8, 1).repeat(8, 2)
     img = (img.astype(np.int32) + rng.integers(-20, 20, img.shape)).clip(0, 255).astype(np.uint8)
-    results = []
-    monkeypatch.setenv("MRCNN_CONV_VGROUP", "0")      # the chained stages load one A tile per tap: same K order on both sides
-    for chain in ("0", "1"):
-        monkeypatch.setenv("MRCNN_CHAIN", chain)
-        cfg = pkg.MaskRCNNConfig()
-        cfg.architecture, cfg.imageShape, cfg.maxProposals, cfg.maxBatch = "resnet50", (size, size, 3), R, 2
-        m = pkg.MaskRCNN(cfg, blobs=blobs, anchors=anchors)
-        try:
-            det, masks = m.prediction_batch(img)
-            results.append((det.copy(), masks.copy()))
-            if chain == "1":
-                continue
-            c = m.ctx.cfg
-            fm = [torch.zeros((2, size // s, size // s, 256), dtype=torch.float16, device="cuda") for s in (4, 8, 16, 32)]
-            probs = torch.zeros((2, anchors.shape[0], 2), device="cuda"); deltas = torch.zeros((2, anchors.shape[0], 4), device="cuda")
-            fp = (C.c_void_p * 4)(*[t.data_ptr() for t in fm])
-            pkg._cabi.check(m.ctx.handle, pkg.lib().mrcnn_backbone_eval(m.ctx.handle, 2, pkg._cabi.ptr(img), fp, probs.data_ptr(), deltas.data_ptr()))
-            fm = [t.cpu().numpy() for t in fm]; probs = probs.cpu().numpy(); deltas = deltas.cpu().numpy()
-            for i in range(2):
-                rois, _, cnt = orc.proposal(probs[i], deltas[i], anchors, pre_nms=6000, max_proposals=R)
-                pooled, _ = orc.pyramid_roialign_nhwc_f16(rois, [f[i] for f in fm], 7, size, size)
-                cls6 = np.zeros((1, R, 6), np.float32)
-                pkg.TimeDistributedClassifierLayer(context=m.ctx).evaluate(
-                    [np.ascontiguousarray(pooled.astype(np.float32).transpose(0, 3, 1, 2))[None]], [cls6])
-                d0, _, n0 = orc.detection(rois, cls6[0])
-                np.testing.assert_array_equal(det[i], d0)
-                pooled14, _ = orc.pyramid_roialign_nhwc_f16(d0, [f[i] for f in fm], 14, size, size)
-                mk = np.zeros((1, 100, 28, 28), np.float32)
-                pkg.TimeDistributedMaskLayer(context=m.ctx).evaluate(
-                    [np.ascontiguousarray(pooled14.astype(np.float32).transpose(0, 3, 1, 2))[None], d0[None]], [mk])
-                np.testing.assert_array_equal(masks[i], mk[0])
-            assert (det[..., 5] > 0).sum() > 0
-        finally:
-            m.close()
-    np.testing.assert_array_equal(results[0][0], results[1][0])
-    np.testing.assert_array_equal(results[0][1], results[1][1])
-
-
-def test_fullsize_chained_stages_bit_identical(pkg, full, monkeypatch):
-    """ResNet101 at 1024x1024: the chained stages (one persistent launch per ResNet stage) give the same detections and
-    masks as the layer-by-layer launches."""
-    monkeypatch.setenv("MRCNN_CONV_VGROUP", "0")
-    _, blobs = pkg.weights.synthetic_blobs(101)
-    outs = []
-    for chain in ("1", "0"):
-        monkeypatch.setenv("MRCNN_CHAIN", chain)
-        cfg = pkg.MaskRCNNConfig()
-        cfg.maxBatch = 2
-        m = pkg.MaskRCNN(cfg, blobs=blobs, anchors=full["anchors"])
-        try:
-            outs.append(m.prediction_batch(full["img"]))
-        finally:
-            m.close()
-    (det, masks), (want_det, want_masks) = outs
-    np.testing.assert_array_equal(det, want_det)
-    np.testing.assert_array_equal(masks, want_masks)
+    cfg = pkg.MaskRCNNConfig()
+    cfg.architecture, cfg.imageShape, cfg.maxProposals, cfg.maxBatch = "resnet50", (size, size, 3), R, 2
+    m = pkg.MaskRCNN(cfg, blobs=blobs, anchors=anchors)
+    try:
+        det, masks = m.prediction_batch(img)
+        fm = [torch.zeros((2, size // s, size // s, 256), dtype=torch.float16, device="cuda") for s in (4, 8, 16, 32)]
+        probs = torch.zeros((2, anchors.shape[0], 2), device="cuda"); deltas = torch.zeros((2, anchors.shape[0], 4), device="cuda")
+        fp = (C.c_void_p * 4)(*[t.data_ptr() for t in fm])
+        pkg._cabi.check(m.ctx.handle, pkg.lib().mrcnn_backbone_eval(m.ctx.handle, 2, pkg._cabi.ptr(img), fp, probs.data_ptr(), deltas.data_ptr()))
+        fm = [t.cpu().numpy() for t in fm]; probs = probs.cpu().numpy(); deltas = deltas.cpu().numpy()
+        for i in range(2):
+            rois, _, cnt = orc.proposal(probs[i], deltas[i], anchors, pre_nms=6000, max_proposals=R)
+            pooled, _ = orc.pyramid_roialign_nhwc_f16(rois, [f[i] for f in fm], 7, size, size)
+            cls6 = np.zeros((1, R, 6), np.float32)
+            pkg.TimeDistributedClassifierLayer(context=m.ctx).evaluate(
+                [np.ascontiguousarray(pooled.astype(np.float32).transpose(0, 3, 1, 2))[None]], [cls6])
+            d0, _, n0 = orc.detection(rois, cls6[0])
+            np.testing.assert_array_equal(det[i], d0)
+            pooled14, _ = orc.pyramid_roialign_nhwc_f16(d0, [f[i] for f in fm], 14, size, size)
+            mk = np.zeros((1, 100, 28, 28), np.float32)
+            pkg.TimeDistributedMaskLayer(context=m.ctx).evaluate(
+                [np.ascontiguousarray(pooled14.astype(np.float32).transpose(0, 3, 1, 2))[None], d0[None]], [mk])
+            np.testing.assert_array_equal(masks[i], mk[0])
+        assert (det[..., 5] > 0).sum() > 0
+    finally:
+        m.close()

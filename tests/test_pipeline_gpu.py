@@ -255,36 +255,12 @@ def test_streaming_misuse_fails_loudly(pkg, small):
     np.testing.assert_array_equal(bufs[0][0].numpy(), bufs[1][0].numpy())
 
 
-def _model_with_env(pkg, monkeypatch, chain, arch=50, size=SIZE, batch=2, pre=1000, props=200):
-    monkeypatch.setenv("MRCNN_CHAIN", "1" if chain else "0")
+def _model_with_env(pkg, monkeypatch, arch=50, size=SIZE, batch=2, pre=1000, props=200):
     _, blobs = pkg.weights.synthetic_blobs(arch)
     cfg = pkg.MaskRCNNConfig()
     cfg.architecture, cfg.imageShape = ("resnet50" if arch == 50 else "resnet101"), (size, size, 3)
     cfg.preNMSMaxProposals, cfg.maxProposals, cfg.maxBatch = pre, props, batch
     return pkg.MaskRCNN(cfg, blobs=blobs, anchors=pkg.synth.generate_anchors(size, size))
-
-
-@pytest.mark.parametrize("batch,lag", [(1, 0), (2, 0), (3, 0), (2, 2), (3, 1)])
-def test_chained_stages_bit_identical_to_layerwise_launches(pkg, small, monkeypatch, batch, lag):
-    """The persistent per-stage chain kernel (conv_chain.cuh: all layers of a ResNet stage in one launch, image-granular
-    dataflow between layers) must reproduce the layer-by-layer launches bit for bit: feature maps, RPN outputs."""
-    monkeypatch.setenv("MRCNN_CHAIN_LAG", str(lag))          # > 0: two halves of the batch `lag` layers apart, zipped segments
-    monkeypatch.setenv("MRCNN_CONV_VGROUP", "0")             # same K order on both sides (the chain kernel loads one A tile per tap)
-    rng = np.random.default_rng(batch)
-    img = rng.integers(0, 256, (batch, SIZE, SIZE, 3), dtype=np.uint8)
-    outs = []
-    for chain in (False, True):
-        model = _model_with_env(pkg, monkeypatch, chain, batch=batch)
-        try:
-            for _ in range(3):                                    # repeated runs: the flags are re-armed every launch
-                fm, probs, deltas = _backbone(pkg, model, img)
-            outs.append((fm, probs, deltas))
-        finally:
-            model.close()
-    for l in range(4):
-        np.testing.assert_array_equal(outs[0][0][l], outs[1][0][l])
-    np.testing.assert_array_equal(outs[0][1], outs[1][1])
-    np.testing.assert_array_equal(outs[0][2], outs[1][2])
 
 
 def test_vertical_tap_groups_same_result_up_to_summation_order(pkg, small, monkeypatch):
@@ -294,8 +270,7 @@ def test_vertical_tap_groups_same_result_up_to_summation_order(pkg, small, monke
     outs = []
     for v in ("0", "1"):
         monkeypatch.setenv("MRCNN_CONV_VGROUP", v)
-        monkeypatch.setenv("MRCNN_CHAIN", "0")
-        model = _model_with_env(pkg, monkeypatch, False, batch=2)
+        model = _model_with_env(pkg, monkeypatch, batch=2)
         try:
             outs.append(_backbone(pkg, model, small["img"]))
         finally:
