@@ -192,8 +192,7 @@ roialign_nhwc_kernel(const float* __restrict__ rois, int roi_stride, int R, Pyra
 // ----------------------------------------------------------------------------------------------------------------
 // TMA-staged NHWC kernel
 // ----------------------------------------------------------------------------------------------------------------
-#define RA_CWARPS 7                // consumer warps (pool 7: one warp per sample column)
-#define RA_THREADS ((RA_CWARPS + 1) * 32)
+// CTA = planner warp (warp 0) + CW consumer warps + row-issuing warp (the last one)
 #define RA_NEG (-(1 << 30))
 
 struct RoiTmaMaps { CUtensorMap m[4][4]; };       // [pyramid level][box width class: 8, 16, 24, 32 pixels]
@@ -203,8 +202,10 @@ struct RoiTmaArgs {
   int C, P;
   const int32_t* level;
   __half* out;
-  int slot_px;                     // widest footprint (pixels) a ring slot holds
-  int slot_bytes;                  // slot_px * C * 2, multiple of 128
+  int slot_px;                     // widest footprint (pixels) the ring takes (wider rois go the gather way)
+  int chunk_bytes;                 // allocation unit of the ring: 8 pixels = 8 * C * 2 bytes (multiple of 128)
+  int nch;                         // chunks in the ring
+  int ahead;                       // rois the producer's L2 prefetch runs ahead of its staging (0: off)
   int box_px[4][4];                // pixels a box of [level][class] really holds (min(8 * (class + 1), W of the level))
   float negzero;                   // -0.0f as a runtime value (see tl::mul2)
   PyramidF16 pyr;
@@ -275,11 +276,14 @@ __device__ __forceinline__ uint4 bilerp8p(uint4 a, uint4 b, uint4 c, uint4 d, fl
 // ---- roi descriptors: written by the producer warp (the only warp that computes the roi's plan), read by the seven
 // consumer warps.  A ring of RA_DESCS descriptors lets the producer run up to RA_DESCS - 1 rois ahead.
 #define RA_DESCS 4
+#define RA_ROWS 32            // row entries (full / empty barrier pairs) of the ring
 #define RA_D_HDR 0            // 32 B: kind, level index, image, pad, y1, x1, y2, x2
 #define RA_D_XTAB 32          // 16 x 16 B: per sample column  {lo tap byte offset, hi tap byte offset, lerp, in range}
 #define RA_D_YTAB 288         // 16 x 32 B: per sample row     {lo slot address, hi slot address, lo barrier, hi barrier,
                               //                                flags, lerp, first ring slot to release, slots to release}
-#define RA_D_BYTES 800
+#define RA_D_ISSUE 800        // 16 B: rows to stage, leftmost column, chunks per row, row bytes (for the issuing warp)
+#define RA_D_ROWS 816         // 32 x 4 B: the distinct tap rows in ascending order
+#define RA_D_BYTES 944
 #define RA_KIND_ZERO 0        // padding roi (or nothing in range): the block is zeros
 #define RA_KIND_RING 1        // rows staged through the ring
 #define RA_KIND_GATHER 2      // the ring cannot hold this roi: taps straight from global memory
@@ -293,27 +297,35 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// PT = pool size known at compile time (7, 14) or 0 (any P <= 16); SLOTS = ring depth; CTAS = CTAs per SM the launch
-// bounds ask for (registers).  Warp 0 = producer, warps 1..7 = consumers; consumer warp w owns sample columns w, w + 7, ...
+// PT = pool size known at compile time (7, 14) or 0 (any P <= 16); CTAS = CTAs per SM the launch bounds ask for
+// (registers); CW = consumer warps.  Warp 0 = planner, warps 1..CW = consumers (consumer warp w owns sample columns
+// w, w + CW, ...), warp CW + 1 = row issuer.  Planning (global reads of the roi, the tap plan, the descriptor) and issuing (waiting for ring space,
+// the TMA loads) are separate warps because one warp doing both was the bottleneck: with the planner a few rois ahead
+// the issuer is only ever blocked on ring space, i.e. the ring stays full.
+// The ring is allocated in chunks of 8 pixels (a row takes 1-4 consecutive chunks, never wrapping: a row that would
+// cross the end starts at chunk 0 and the tail is skipped) with one full / empty barrier pair per ROW (RA_ROWS row
+// entries), so narrow rows do not occupy the space of wide ones and about twice as many rows are in flight as with
+// fixed slots -- the kernel's speed is set by the bytes it keeps in flight.
 // The loop over sample rows stays rolled on purpose: an unrolled variant (4096 instructions) was instruction-fetch
 // bound (ncu: stall_no_inst on top), see DESIGN.md.
-template <int PT, int SLOTS, int CTAS>
-__global__ void __launch_bounds__(RA_THREADS, CTAS)
+template <int PT, int CW, int CTAS>
+__global__ void __launch_bounds__((CW + 2) * 32, CTAS)
 roialign_nhwc_tma_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaArgs a) {
+  constexpr int SLOTS = RA_ROWS;
   extern __shared__ uint8_t ra_smem[];
   __shared__ __align__(8) uint64_t s_full[SLOTS], s_empty[SLOTS], s_dfull[RA_DESCS], s_dempty[RA_DESCS];
+  __shared__ uint8_t s_chunks_of[SLOTS];                      // producer: chunks held by the row in each row entry
   __shared__ __align__(16) uint8_t s_desc[RA_DESCS * RA_D_BYTES];
-  __shared__ int s_rows[32];                                  // producer: the current roi's distinct tap rows
   __shared__ int g_lo[2][64], g_hi[2][64];                    // gather path: per-axis taps of the current roi
   __shared__ float g_lerp[2][64];
-  constexpr int NPX = PT ? (PT + RA_CWARPS - 1) / RA_CWARPS : 3;     // sample columns per consumer warp
+  constexpr int NPX = PT ? (PT + CW - 1) / CW : 3;     // sample columns per consumer warp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t slots = (tl::smem_u32(ra_smem) + 127u) & ~127u;
   const uint32_t full0 = tl::smem_u32(s_full), empty0 = tl::smem_u32(s_empty);
   const uint32_t dfull0 = tl::smem_u32(s_dfull), dempty0 = tl::smem_u32(s_dempty), desc0 = tl::smem_u32(s_desc);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < SLOTS; ++s) { tl::mbar_init(full0 + 8 * s, 1); tl::mbar_init(empty0 + 8 * s, RA_CWARPS); }
-    for (int s = 0; s < RA_DESCS; ++s) { tl::mbar_init(dfull0 + 8 * s, 1); tl::mbar_init(dempty0 + 8 * s, RA_CWARPS); }
+    for (int s = 0; s < SLOTS; ++s) { tl::mbar_init(full0 + 8 * s, 1); tl::mbar_init(empty0 + 8 * s, CW); }
+    for (int s = 0; s < RA_DESCS; ++s) { tl::mbar_init(dfull0 + 8 * s, 1); tl::mbar_init(dempty0 + 8 * s, CW + 1); }
     tl::fence_barrier_init();
   }
   __syncthreads();
@@ -322,9 +334,11 @@ roialign_nhwc_tma_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaAr
   const uint32_t pix = (uint32_t)C * 2u;
 
   if (warp == 0) {
-    // ---------------- producer: plan -> descriptor -> row loads ----------------
-    uint32_t seq = 0;                                         // rows staged so far
+    // ---------------- planner: roi -> plan -> descriptor (runs up to RA_DESCS - 1 rois ahead) ----------------
+    uint32_t seq = 0;                                         // rows planned so far (row n uses row entry n % RA_ROWS)
     uint32_t n = 0;                                           // rois described so far
+    uint32_t cursor = 0;                                      // ring chunk the next row starts at (same rule as the issuer)
+    const uint32_t NCH = (uint32_t)a.nch;
     #pragma unroll 1
     for (int item = blockIdx.x; item < a.total; item += stride, ++n) {
       const uint32_t d = desc0 + (n % RA_DESCS) * RA_D_BYTES;
@@ -334,10 +348,22 @@ roialign_nhwc_tma_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaAr
       const int m = lv >= 0 ? lv - 2 : 0;
       LanePlan p = roi_lane_plan(y1, x1, y2, x2, a.pyr.h[m], a.pyr.w[m], P, lane, a.slot_px);
       const int kind = lv < 0 ? RA_KIND_ZERO : (!p.regular ? RA_KIND_GATHER : ((p.nrows == 0 || p.nx == 0) ? RA_KIND_ZERO : RA_KIND_RING));
-      tl::mbar_wait(dempty0 + 8 * (n % RA_DESCS), ((n / RA_DESCS) & 1) ^ 1);     // the consumers are done with this descriptor
+      // chunks per row of this roi, and where row j of the roi lands: rows are placed one after the other from the
+      // cursor; a row that would cross the end of the ring starts at chunk 0 instead
+      const uint32_t k = kind == RA_KIND_RING ? (uint32_t)((p.nx + 7) / 8) : 1u;
+      const uint32_t r0 = (NCH - cursor) / k, per_lap = NCH / k;
+      auto row_chunk = [&](uint32_t j) -> uint32_t { return j < r0 ? cursor + j * k : ((j - r0) % per_lap) * k; };
+      const int img = item / a.R;
+      if (a.ahead > 0 && kind == RA_KIND_RING && lane < 16) {       // optional: ask L2 for the rows now (the issuer is 1-3 rois behind)
+        const CUtensorMap* tm = &maps.m[m][k - 1];
+        if (p.new_lo) tl::tma_prefetch_4d(tm, 0, p.x0, p.lo, img);
+        if (p.new_hi) tl::tma_prefetch_4d(tm, 0, p.x0, p.hi, img);
+      }
+      tl::mbar_wait(dempty0 + 8 * (n % RA_DESCS), ((n / RA_DESCS) & 1) ^ 1);     // consumers + issuer are done with this descriptor
       if (lane == 0) {
-        sts128(d + RA_D_HDR, (uint32_t)kind, (uint32_t)m, (uint32_t)(item / a.R), 0u);
+        sts128(d + RA_D_HDR, (uint32_t)kind, (uint32_t)m, (uint32_t)img, 0u);
         sts128(d + RA_D_HDR + 16, __float_as_uint(y1), __float_as_uint(x1), __float_as_uint(y2), __float_as_uint(x2));
+        sts128(d + RA_D_ISSUE, kind == RA_KIND_RING ? (uint32_t)p.nrows : 0u, (uint32_t)p.x0, k, (uint32_t)a.box_px[m][k - 1] * pix);
       }
       if (kind == RA_KIND_RING) {
         const int i = lane & 15;
@@ -348,42 +374,69 @@ roialign_nhwc_tma_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaAr
         const int next_pos_lo = __shfl_down_sync(0xffffffffu, p.pos_lo, 1, 16);
         if (lane < 16 && i < P) {
           const uint32_t qlo = seq + p.pos_lo, qhi = seq + p.pos_hi;
-          const uint32_t slo = qlo % SLOTS, shi = qhi % SLOTS;
+          const uint32_t elo = qlo % SLOTS, ehi = qhi % SLOTS;
           const bool wlo = p.ok && (i == 0 || !prev_ok || p.pos_lo > prev_pos_hi), whi = p.ok && p.pos_hi > p.pos_lo;
           const uint32_t flags = ((qlo / SLOTS) & 1u) | (((qhi / SLOTS) & 1u) << 1) | (p.ok ? RA_F_YOK : 0u) |
                                  (wlo ? RA_F_WAIT_LO : 0u) | (whi ? RA_F_WAIT_HI : 0u);
           const int rel0 = i == 0 ? 0 : p.pos_lo, rel1 = i + 1 < P ? next_pos_lo : p.nrows;
-          sts128(d + RA_D_YTAB + 32 * i, slots + slo * a.slot_bytes, slots + shi * a.slot_bytes, full0 + 8 * slo, full0 + 8 * shi);
+          sts128(d + RA_D_YTAB + 32 * i, slots + row_chunk((uint32_t)p.pos_lo) * a.chunk_bytes,
+                 slots + row_chunk((uint32_t)p.pos_hi) * a.chunk_bytes, full0 + 8 * elo, full0 + 8 * ehi);
           sts128(d + RA_D_YTAB + 32 * i + 16, flags, __float_as_uint(p.lerp), (seq + rel0) % SLOTS, (uint32_t)(rel1 - rel0));
-          if (p.new_lo) s_rows[p.base] = p.lo;
-          if (p.new_hi) s_rows[p.base + p.new_lo] = p.hi;
+          if (p.new_lo) tl::sts32(d + RA_D_ROWS + 4 * p.base, (uint32_t)p.lo);
+          if (p.new_hi) tl::sts32(d + RA_D_ROWS + 4 * (p.base + p.new_lo), (uint32_t)p.hi);
         }
       }
       __syncwarp();
-      if (lane == 0) {
-        tl::mbar_arrive(dfull0 + 8 * (n % RA_DESCS));
-        if (kind == RA_KIND_RING) {
-          const int wc = (p.nx + 7) / 8 - 1;
-          const CUtensorMap* tm = &maps.m[m][wc];
-          const uint32_t bytes = (uint32_t)a.box_px[m][wc] * pix;
-          const int img = item / a.R;
-          #pragma unroll 1
-          for (int j = 0; j < p.nrows; ++j) {
-            const uint32_t q = seq + j, sl = q % SLOTS;
-            tl::mbar_wait(empty0 + 8 * sl, ((q / SLOTS) & 1) ^ 1);
-            tl::mbar_expect_tx(full0 + 8 * sl, bytes);
-            tl::tma_load_4d(slots + sl * a.slot_bytes, tm, full0 + 8 * sl, 0, p.x0, s_rows[j], img);
+      if (lane == 0) tl::mbar_arrive(dfull0 + 8 * (n % RA_DESCS));
+      if (kind == RA_KIND_RING) {
+        seq += p.nrows;
+        const uint32_t last = row_chunk((uint32_t)p.nrows - 1) + k;
+        cursor = last == NCH ? 0 : last;
+      }
+    }
+    return;
+  }
+
+  if (warp == CW + 1) {
+    // ---------------- row issuer (one lane): descriptor -> ring space -> TMA row loads ----------------
+    if (lane == 0) {
+      uint32_t seq = 0, n = 0, cursor = 0, free_chunks = (uint32_t)a.nch, head_row = 0;
+      const uint32_t NCH = (uint32_t)a.nch;
+      #pragma unroll 1
+      for (int item = blockIdx.x; item < a.total; item += stride, ++n) {
+        const uint32_t d = desc0 + (n % RA_DESCS) * RA_D_BYTES;
+        tl::mbar_wait(dfull0 + 8 * (n % RA_DESCS), (n / RA_DESCS) & 1);
+        const uint4 hdr = tl::lds128(d + RA_D_HDR), is = tl::lds128(d + RA_D_ISSUE);
+        const uint32_t nrows = is.x, k = is.z, bytes = is.w;
+        const int x0 = (int)is.y, img = (int)hdr.z;
+        const CUtensorMap* tm = &maps.m[hdr.y][k - 1];
+        #pragma unroll 1
+        for (uint32_t j = 0; j < nrows; ++j) {
+          uint32_t c = cursor, need = k;
+          if (c + k > NCH) { need += NCH - c; c = 0; }                       // skip the tail of the ring
+          while (free_chunks < need || seq - head_row >= (uint32_t)SLOTS) {
+            const uint32_t e = head_row % SLOTS;                              // oldest row in flight: wait until it is released
+            tl::mbar_wait(empty0 + 8 * e, (head_row / SLOTS) & 1);
+            free_chunks += s_chunks_of[e];
+            ++head_row;
           }
+          free_chunks -= need;
+          cursor = c + k == NCH ? 0 : c + k;
+          const uint32_t e = seq % SLOTS;
+          s_chunks_of[e] = (uint8_t)need;
+          const int row = (int)tl::lds32u(d + RA_D_ROWS + 4 * j);
+          tl::mbar_expect_tx(full0 + 8 * e, bytes);
+          tl::tma_load_4d(slots + c * a.chunk_bytes, tm, full0 + 8 * e, 0, x0, row, img);
+          ++seq;
         }
+        tl::mbar_arrive(dempty0 + 8 * (n % RA_DESCS));
       }
-      if (kind == RA_KIND_RING) seq += p.nrows;
-      __syncwarp();
     }
     return;
   }
 
   // ---------------- consumers ----------------
-  const int cw = warp - 1, ct = threadIdx.x - 32, nct = RA_CWARPS * 32;
+  const int cw = warp - 1, ct = threadIdx.x - 32, nct = CW * 32;
   const uint4 z = make_uint4(0, 0, 0, 0);
   const float nz = a.negzero;
   const bool lane_on = lane < cvec;                           // C < 256: the upper lanes have no channels
@@ -399,7 +452,7 @@ roialign_nhwc_tma_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaAr
       uint4 xe[NPX];
       #pragma unroll
       for (int k = 0; k < NPX; ++k) {
-        const int px = cw + k * RA_CWARPS;
+        const int px = cw + k * CW;
         xe[k] = px < P ? tl::lds128(d + RA_D_XTAB + 16 * px) : z;
         xe[k].x += (uint32_t)lane * 16u; xe[k].y += (uint32_t)lane * 16u;
         if (!lane_on) xe[k].w = 0;
@@ -414,14 +467,14 @@ roialign_nhwc_tma_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaAr
         if (e1.x & RA_F_WAIT_HI) tl::mbar_wait_nc(e0.w, (e1.x >> 1) & 1u);
         #pragma unroll
         for (int k = 0; k < NPX; ++k) {
-          if (cw + k * RA_CWARPS < P && lane_on) {
+          if (cw + k * CW < P && lane_on) {
             uint4 r = z;
             if (yok && xe[k].w) {
               const uint4 ta = tl::lds128(e0.x + xe[k].x), tb = tl::lds128(e0.x + xe[k].y);
               const uint4 tc = tl::lds128(e0.y + xe[k].x), td = tl::lds128(e0.y + xe[k].y);
               r = bilerp8p(ta, tb, tc, td, __uint_as_float(xe[k].z), ly, nz);
             }
-            od[(size_t)k * RA_CWARPS * cvec] = r;
+            od[(size_t)k * CW * cvec] = r;
           }
         }
         od += (size_t)P * cvec;
@@ -449,7 +502,7 @@ roialign_nhwc_tma_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaAr
         }
       }
       tl::named_bar_sync(1, nct);
-      for (int s = cw; s < PP; s += RA_CWARPS) {
+      for (int s = cw; s < PP; s += CW) {
         const int py = s / P, px = s - py * P;
         const int yl = g_lo[0][py], yh = g_hi[0][py], xl = g_lo[1][px], xh = g_hi[1][px];
         const bool ok = yl >= 0 && xl >= 0;
@@ -521,7 +574,7 @@ struct RoiTmaEntry {                 // tensor maps of one pyramid (they do not 
   const void* p[4]; int hw[8]; int C, batch;
   RoiTmaMaps maps; int box_px[4][4];
 };
-struct RoiTmaCache { std::vector<RoiTmaEntry> entries; int slots = 8; int slot_px = 0; int mode = -1; };
+struct RoiTmaCache { std::vector<RoiTmaEntry> entries; int ctas = 2; int cw = 7; int slot_px = 0; int mode = -1; int ahead = 0; };
 
 void roialign_release(mrcnn_ctx* ctx) {
   delete (RoiTmaCache*)ctx->roi_tma;
@@ -564,31 +617,53 @@ static int roi_tma_entry(mrcnn_ctx* ctx, RoiTmaCache* cache, int batch, const __
   return MRCNN_OK;
 }
 
-template <int PT, int SLOTS, int CTAS>
-static int launch_roialign_tma_t(mrcnn_ctx* ctx, const RoiTmaMaps& maps, const RoiTmaArgs& a) {
-  auto kern = roialign_nhwc_tma_kernel<PT, SLOTS, CTAS>;
-  const int smem = SLOTS * a.slot_bytes + 128;
+template <int PT, int CW, int CTAS>
+static int launch_roialign_tma_t(mrcnn_ctx* ctx, const RoiTmaMaps& maps, RoiTmaArgs a) {
+  auto kern = roialign_nhwc_tma_kernel<PT, CW, CTAS>;
+  constexpr int threads = (CW + 2) * 32;
+  // ring size: what CTAS resident CTAs leave of the SM's shared memory (static part ~6.7 KB + 1 KB reserved per CTA)
+  const int budget = (228 * 1024) / CTAS - 1024 - 7168 - 128;
+  a.nch = std::min(budget / a.chunk_bytes, 255);
+  if (a.nch * 8 < a.slot_px * 2) return mrcnn_fail(ctx, MRCNN_EINVAL, "roialign: too many channels for the staged kernel's ring");
+  const int smem = a.nch * a.chunk_bytes + 128;
   static int per_sm_cached[64] = {0};
   static int smem_cached[64] = {0};
   const int dv = ctx->device & 63;
   if (smem_cached[dv] != smem) {
     MRCNN_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    MRCNN_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached[dv], kern, RA_THREADS, smem));
+    MRCNN_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached[dv], kern, threads, smem));
     smem_cached[dv] = smem;
   }
   const int per_sm = per_sm_cached[dv];
   if (per_sm < 1) return mrcnn_fail(ctx, MRCNN_ECUDA, "roialign: the staged kernel does not fit on an SM");
   const int grid = (int)std::min<int64_t>((int64_t)a.total, (int64_t)per_sm * ctx->sm_count);
-  kern<<<grid, RA_THREADS, smem, ctx->stream>>>(maps, a);
+  kern<<<grid, threads, smem, ctx->stream>>>(maps, a);
   return MRCNN_OK;
 }
 
 static int launch_roialign_tma(mrcnn_ctx* ctx, RoiTmaCache* cache, const RoiTmaMaps& maps, const RoiTmaArgs& a) {
-  // ring depth / residency: 8 slots, 2 CTAs per SM (default) or 5 slots, 3 CTAs per SM (MRCNN_ROIALIGN_SLOTS=5)
-  const bool three = cache->slots == 5 && 5 * a.slot_bytes + 128 + 4096 <= 75 * 1024;
-  if (a.P == 7) return three ? launch_roialign_tma_t<7, 5, 3>(ctx, maps, a) : launch_roialign_tma_t<7, 8, 2>(ctx, maps, a);
-  if (a.P == 14) return three ? launch_roialign_tma_t<14, 5, 3>(ctx, maps, a) : launch_roialign_tma_t<14, 8, 2>(ctx, maps, a);
-  return launch_roialign_tma_t<0, 8, 2>(ctx, maps, a);
+  // MRCNN_ROIALIGN_CTAS / MRCNN_ROIALIGN_CW pick the residency and the consumer-warp count (experiments; the defaults
+  // are what measured fastest)
+  const int v = cache->ctas * 10 + cache->cw;
+  if (a.P == 7) {
+    switch (v) {
+      case 27: return launch_roialign_tma_t<7, 7, 2>(ctx, maps, a);
+      case 37: return launch_roialign_tma_t<7, 7, 3>(ctx, maps, a);
+      case 24: return launch_roialign_tma_t<7, 4, 2>(ctx, maps, a);
+      case 34: return launch_roialign_tma_t<7, 4, 3>(ctx, maps, a);
+      case 44: return launch_roialign_tma_t<7, 4, 4>(ctx, maps, a);
+    }
+    return launch_roialign_tma_t<7, 7, 2>(ctx, maps, a);
+  }
+  if (a.P == 14) {
+    switch (v) {
+      case 37: return launch_roialign_tma_t<14, 7, 3>(ctx, maps, a);
+      case 24: return launch_roialign_tma_t<14, 4, 2>(ctx, maps, a);   // 4 columns per warp
+      case 34: return launch_roialign_tma_t<14, 4, 3>(ctx, maps, a);
+    }
+    return launch_roialign_tma_t<14, 7, 2>(ctx, maps, a);
+  }
+  return launch_roialign_tma_t<0, 7, 2>(ctx, maps, a);
 }
 
 int roialign_nhwc_f16_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int roi_stride, int64_t R,
@@ -611,10 +686,14 @@ int roialign_nhwc_f16_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int ro
     const char* e = getenv("MRCNN_ROIALIGN");                 // "gather": the pure gather kernel (A/B measurements, tests)
     cache->mode = (e && !strcmp(e, "gather")) ? 0 : 1;
     const char* es = getenv("MRCNN_ROIALIGN_SLOT_PX");        // ring slot width in pixels (8, 16, 24 or 32)
-    cache->slot_px = es ? atoi(es) : 24;
-    if (cache->slot_px != 8 && cache->slot_px != 16 && cache->slot_px != 24 && cache->slot_px != 32) cache->slot_px = 24;
-    const char* en = getenv("MRCNN_ROIALIGN_SLOTS");          // 5: shallower ring, three CTAs per SM
-    cache->slots = (en && atoi(en) == 5) ? 5 : 8;
+    cache->slot_px = es ? atoi(es) : 32;
+    if (cache->slot_px != 8 && cache->slot_px != 16 && cache->slot_px != 24 && cache->slot_px != 32) cache->slot_px = 32;
+    const char* en = getenv("MRCNN_ROIALIGN_CTAS");           // 3: three CTAs per SM with smaller rings
+    cache->ctas = en ? std::max(2, std::min(4, atoi(en))) : 2;
+    const char* ew = getenv("MRCNN_ROIALIGN_CW");             // consumer warps per CTA (7 or 4)
+    cache->cw = (ew && atoi(ew) == 4) ? 4 : 7;
+    const char* ea = getenv("MRCNN_ROIALIGN_AHEAD");          // rois the producer's L2 prefetch runs ahead (0 = off)
+    cache->ahead = ea ? std::max(0, std::min(16, atoi(ea))) : 0;
   }
   // bytes this launch has to move at least: the output once + the rois; the map bytes the rois really touch are
   // data dependent (bench.py reports them from the roi footprints and, under ncu, from dram__bytes)
@@ -626,7 +705,7 @@ int roialign_nhwc_f16_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int ro
     RoiTmaArgs a;
     a.rois = d_rois; a.roi_stride = roi_stride; a.R = (int)R; a.total = (int)(batch * R);
     a.C = (int)C; a.P = P; a.level = lv; a.out = d_out;
-    a.slot_px = cache->slot_px; a.slot_bytes = cache->slot_px * (int)C * 2;
+    a.slot_px = cache->slot_px; a.chunk_bytes = 8 * (int)C * 2; a.nch = 0; a.ahead = cache->ahead;
     memcpy(a.box_px, e->box_px, sizeof(a.box_px));
     a.negzero = -0.0f; a.pyr = pyr;
     rc = launch_roialign_tma(ctx, cache, e->maps, a);
