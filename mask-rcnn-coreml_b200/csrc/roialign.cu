@@ -27,8 +27,9 @@
 #include <string.h>
 
 __global__ void roi_level_kernel(const float* __restrict__ rois, int roi_stride, int64_t total,
-                                 double ratio, int32_t* __restrict__ level) {
+                                 double ratio, int32_t* __restrict__ level, int32_t* __restrict__ ticket) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *ticket = 0;               // work counter of the staged kernel that follows on the stream
   if (i >= total) return;
   const float* r = rois + i * roi_stride;
   double y1 = r[0], x1 = r[1], y2 = r[2], x2 = r[3];
@@ -195,7 +196,7 @@ roialign_nhwc_kernel(const float* __restrict__ rois, int roi_stride, int R, Pyra
 // CTA = planner warp (warp 0) + CW consumer warps + row-issuing warp (the last one)
 #define RA_NEG (-(1 << 30))
 
-struct RoiTmaMaps { CUtensorMap m[4][4]; };       // [pyramid level][box width class: 8, 16, 24, 32 pixels]
+struct RoiTmaMaps { CUtensorMap m[4][8]; };       // [pyramid level][box width class k - 1: k chunks of cpx (4 or 8) pixels]
 
 struct RoiTmaArgs {
   const float* rois; int roi_stride; int R; int total;      // total = batch * R
@@ -205,8 +206,10 @@ struct RoiTmaArgs {
   int slot_px;                     // widest footprint (pixels) the ring takes (wider rois go the gather way)
   int chunk_bytes;                 // allocation unit of the ring: 8 pixels = 8 * C * 2 bytes (multiple of 128)
   int nch;                         // chunks in the ring
-  int ahead;                       // rois the producer's L2 prefetch runs ahead of its staging (0: off)
-  int box_px[4][4];                // pixels a box of [level][class] really holds (min(8 * (class + 1), W of the level))
+  int ahead;                       // 1: the planner asks L2 for a roi's rows when it plans it (0: off)
+  int* ticket;                     // work counter, zeroed by the level kernel: rois are handed out in order, one at a time
+  int box_px[4][8];                // pixels a box of [level][class] really holds (min(cpx * (class + 1), W of the level))
+  int cpx;                         // pixels per ring chunk: 4 (C % 16 == 0, so that a chunk is a multiple of 128 B) or 8
   float negzero;                   // -0.0f as a runtime value (see tl::mul2)
   PyramidF16 pyr;
 };
@@ -273,28 +276,60 @@ __device__ __forceinline__ uint4 bilerp8p(uint4 a, uint4 b, uint4 c, uint4 d, fl
                     bilerp2p(a.z, b.z, c.z, d.z, lx, ly, nz), bilerp2p(a.w, b.w, c.w, d.w, lx, ly, nz));
 }
 
-// ---- roi descriptors: written by the producer warp (the only warp that computes the roi's plan), read by the seven
-// consumer warps.  A ring of RA_DESCS descriptors lets the producer run up to RA_DESCS - 1 rois ahead.
+// ---- roi descriptors: written by the planner warp (the only warp that computes the roi's plan), read by the consumer
+// warps and the row issuer.  A ring of RA_DESCS descriptors lets the planner run up to RA_DESCS - 1 rois ahead.
 #define RA_DESCS 4
 #define RA_ROWS 32            // row entries (full / empty barrier pairs) of the ring
-#define RA_D_HDR 0            // 32 B: kind, level index, image, pad, y1, x1, y2, x2
-#define RA_D_XTAB 32          // 16 x 16 B: per sample column  {lo tap byte offset, hi tap byte offset, lerp, in range}
-#define RA_D_YTAB 288         // 16 x 32 B: per sample row     {lo slot address, hi slot address, lo barrier, hi barrier,
-                              //                                flags, lerp, first ring slot to release, slots to release}
-#define RA_D_ISSUE 800        // 16 B: rows to stage, leftmost column, chunks per row, row bytes (for the issuing warp)
-#define RA_D_ROWS 816         // 32 x 4 B: the distinct tap rows in ascending order
-#define RA_D_BYTES 944
+#define RA_D_HDR 0            // 32 B: kind, level index, image, distinct rows | y1, x1, y2, x2
+#define RA_D_HDR2 32          // 16 B: row entry of the roi's first row, leading out-of-range sample rows, in-range sample rows
+#define RA_D_XTAB 48          // 16 x 16 B per sample column: lo tap byte offset, hi tap byte offset, lerp, in range
+#define RA_D_RTAB 304         // row-wise loop: 32 x 16 B per distinct row (ascending): ring address, full barrier, parity to wait for
+#define RA_D_YTAB 816         //               16 x 8 B per sample row: lerp, lo row == hi row
+#define RA_D_STAB 304         // sample-row loop (same bytes as RTAB / YTAB): 16 x 48 B per sample row:
+                              //   lo row address, hi row address, lo full barrier, hi full barrier |
+                              //   lo parity, hi parity, lerp, in range | empty barrier to arrive on (0: none) x 2
+#define RA_D_ISSUE 1072       // 16 B for the issuing warp: rows to stage, leftmost column, chunks per row, row bytes
+#define RA_D_ROWS 1088        // 32 x 4 B: the distinct tap rows (feature-map row indices)
+#define RA_D_ETAB 1216       // 32 x 4 B per distinct row: sample rows COMPLETED by this row (their hi tap): first | count << 8
+#define RA_D_BYTES 1344
 #define RA_KIND_ZERO 0        // padding roi (or nothing in range): the block is zeros
 #define RA_KIND_RING 1        // rows staged through the ring
 #define RA_KIND_GATHER 2      // the ring cannot hold this roi: taps straight from global memory
-#define RA_F_PAR_LO 1u        // parity to wait for on the lo / hi row's full barrier
-#define RA_F_PAR_HI 2u
-#define RA_F_YOK 4u           // sample row in range
-#define RA_F_WAIT_LO 8u       // first use of the lo / hi row: its full barrier has to be waited for
-#define RA_F_WAIT_HI 16u
+#define RA_KIND_RING_FAST 3   // RA_KIND_RING with every sample in range (and C == 256): the loop without predicates
+#define RA_KIND_END 4         // no more rois: every role leaves its loop
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// x-lerp of one staged feature row at one sample column, for this lane's 8 channels:  H = l + (r - l) * lx -- the `top`
+// (or `bot`) term of crop_and_resize.  It is evaluated once per (row, column): a row that is the bottom tap of one sample
+// row and the top tap of the next is not interpolated twice, and the row's shared memory is free again right after.
+struct HRow { float2 v[4]; };
+
+__device__ __forceinline__ HRow hrow(uint32_t row_addr, uint32_t xl_off, uint32_t xh_off, float lx, float nz) {
+  const uint4 l = tl::lds128(row_addr + xl_off), r = tl::lds128(row_addr + xh_off);
+  const uint32_t lw[4] = {l.x, l.y, l.z, l.w}, rw[4] = {r.x, r.y, r.z, r.w};
+  HRow h;
+  #pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
+    const float2 fr = __half22float2(*reinterpret_cast<const __half2*>(&rw[i]));
+    h.v[i] = tl::add2(fl, tl::mul2(tl::sub2(fr, fl), lx, nz));
+  }
+  return h;
+}
+
+// out = top + (bot - top) * ly, rounded to fp16 (top == bot when the sample row sits exactly on a feature row)
+__device__ __forceinline__ uint4 ylerp_pack(const HRow& top, const HRow& bot, float ly, float nz) {
+  uint32_t o[4];
+  #pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 r = tl::add2(top.v[i], tl::mul2(tl::sub2(bot.v[i], top.v[i]), ly, nz));
+    const __half2 hh = __floats2half2_rn(r.x, r.y);
+    o[i] = *reinterpret_cast<const uint32_t*>(&hh);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // PT = pool size known at compile time (7, 14) or 0 (any P <= 16); CTAS = CTAs per SM the launch bounds ask for
@@ -308,7 +343,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 // fixed slots -- the kernel's speed is set by the bytes it keeps in flight.
 // The loop over sample rows stays rolled on purpose: an unrolled variant (4096 instructions) was instruction-fetch
 // bound (ncu: stall_no_inst on top), see DESIGN.md.
-template <int PT, int CW, int CTAS>
+template <int PT, int CW, int CTAS, bool ROWWISE>
 __global__ void __launch_bounds__((CW + 2) * 32, CTAS)
 roialign_nhwc_tma_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaArgs a) {
   constexpr int SLOTS = RA_ROWS;
@@ -330,7 +365,6 @@ roialign_nhwc_tma_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaAr
   }
   __syncthreads();
   const int C = a.C, P = PT ? PT : a.P, PP = P * P, cvec = C >> 3;
-  const int stride = gridDim.x;
   const uint32_t pix = (uint32_t)C * 2u;
 
   if (warp == 0) {
@@ -340,55 +374,87 @@ roialign_nhwc_tma_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaAr
     uint32_t cursor = 0;                                      // ring chunk the next row starts at (same rule as the issuer)
     const uint32_t NCH = (uint32_t)a.nch;
     #pragma unroll 1
-    for (int item = blockIdx.x; item < a.total; item += stride, ++n) {
+    for (;; ++n) {
+      // next roi: a ticket (rois in order; CTAs that drew cheap rois simply draw more of them -- no tail of unlucky CTAs)
+      int item = 0;
+      if (lane == 0) item = atomicAdd(a.ticket, 1);
+      item = __shfl_sync(0xffffffffu, item, 0);
       const uint32_t d = desc0 + (n % RA_DESCS) * RA_D_BYTES;
+      if (item >= a.total) {
+        tl::mbar_wait(dempty0 + 8 * (n % RA_DESCS), ((n / RA_DESCS) & 1) ^ 1);
+        if (lane == 0) { sts128(d + RA_D_HDR, RA_KIND_END, 0u, 0u, 0u); sts128(d + RA_D_ISSUE, 0u, 0u, 1u, 0u); tl::mbar_arrive(dfull0 + 8 * (n % RA_DESCS)); }
+        break;
+      }
       const float* rr = a.rois + (int64_t)item * a.roi_stride;
       const int lv = __ldg(a.level + item);
       const float y1 = __ldg(rr), x1 = __ldg(rr + 1), y2 = __ldg(rr + 2), x2 = __ldg(rr + 3);
       const int m = lv >= 0 ? lv - 2 : 0;
       LanePlan p = roi_lane_plan(y1, x1, y2, x2, a.pyr.h[m], a.pyr.w[m], P, lane, a.slot_px);
-      const int kind = lv < 0 ? RA_KIND_ZERO : (!p.regular ? RA_KIND_GATHER : ((p.nrows == 0 || p.nx == 0) ? RA_KIND_ZERO : RA_KIND_RING));
+      const unsigned allok = __ballot_sync(0xffffffffu, (lane & 15) >= P || p.ok);
+      int kind = lv < 0 ? RA_KIND_ZERO : (!p.regular ? RA_KIND_GATHER : ((p.nrows == 0 || p.nx == 0) ? RA_KIND_ZERO : RA_KIND_RING));
+      const bool ring = kind == RA_KIND_RING;
+      if (!ROWWISE && ring && allok == 0xffffffffu && cvec == 32) kind = RA_KIND_RING_FAST;
       // chunks per row of this roi, and where row j of the roi lands: rows are placed one after the other from the
       // cursor; a row that would cross the end of the ring starts at chunk 0 instead
-      const uint32_t k = kind == RA_KIND_RING ? (uint32_t)((p.nx + 7) / 8) : 1u;
+      const uint32_t k = ring ? (uint32_t)((p.nx + a.cpx - 1) / a.cpx) : 1u;
       const uint32_t r0 = (NCH - cursor) / k, per_lap = NCH / k;
       auto row_chunk = [&](uint32_t j) -> uint32_t { return j < r0 ? cursor + j * k : ((j - r0) % per_lap) * k; };
       const int img = item / a.R;
-      if (a.ahead > 0 && kind == RA_KIND_RING && lane < 16) {       // optional: ask L2 for the rows now (the issuer is 1-3 rois behind)
+      if (a.ahead > 0 && ring && lane < 16) {       // optional: ask L2 for the rows now (the issuer is 1-3 rois behind)
         const CUtensorMap* tm = &maps.m[m][k - 1];
         if (p.new_lo) tl::tma_prefetch_4d(tm, 0, p.x0, p.lo, img);
         if (p.new_hi) tl::tma_prefetch_4d(tm, 0, p.x0, p.hi, img);
       }
       tl::mbar_wait(dempty0 + 8 * (n % RA_DESCS), ((n / RA_DESCS) & 1) ^ 1);     // consumers + issuer are done with this descriptor
+      const unsigned yvalid = __ballot_sync(0xffffffffu, lane < 16 && p.ok);
       if (lane == 0) {
-        sts128(d + RA_D_HDR, (uint32_t)kind, (uint32_t)m, (uint32_t)img, 0u);
+        sts128(d + RA_D_HDR, (uint32_t)kind, (uint32_t)m, (uint32_t)img, ring ? (uint32_t)p.nrows : 0u);
         sts128(d + RA_D_HDR + 16, __float_as_uint(y1), __float_as_uint(x1), __float_as_uint(y2), __float_as_uint(x2));
-        sts128(d + RA_D_ISSUE, kind == RA_KIND_RING ? (uint32_t)p.nrows : 0u, (uint32_t)p.x0, k, (uint32_t)a.box_px[m][k - 1] * pix);
+        sts128(d + RA_D_HDR2, seq % SLOTS, yvalid ? (uint32_t)(__ffs(yvalid) - 1) : (uint32_t)P, (uint32_t)__popc(yvalid), (uint32_t)item);
+        sts128(d + RA_D_ISSUE, ring ? (uint32_t)p.nrows : 0u, (uint32_t)p.x0, k, (uint32_t)a.box_px[m][k - 1] * pix);
       }
-      if (kind == RA_KIND_RING) {
+      if (ring) {
         const int i = lane & 15;
+        if (ROWWISE) tl::sts32(d + RA_D_ETAB + 4 * lane, 0u);
+        const int prev_ok = __shfl_up_sync(0xffffffffu, p.ok, 1, 16), next_pos_lo = __shfl_down_sync(0xffffffffu, p.pos_lo, 1, 16);
+        __syncwarp();
         if (lane >= 16) {
           if (i < P) sts128(d + RA_D_XTAB + 16 * i, (uint32_t)(p.lo - p.x0) * pix, (uint32_t)(p.hi - p.x0) * pix, __float_as_uint(p.lerp), (uint32_t)p.ok);
-        }
-        const int prev_ok = __shfl_up_sync(0xffffffffu, p.ok, 1, 16), prev_pos_hi = __shfl_up_sync(0xffffffffu, p.pos_hi, 1, 16);
-        const int next_pos_lo = __shfl_down_sync(0xffffffffu, p.pos_lo, 1, 16);
-        if (lane < 16 && i < P) {
-          const uint32_t qlo = seq + p.pos_lo, qhi = seq + p.pos_hi;
-          const uint32_t elo = qlo % SLOTS, ehi = qhi % SLOTS;
-          const bool wlo = p.ok && (i == 0 || !prev_ok || p.pos_lo > prev_pos_hi), whi = p.ok && p.pos_hi > p.pos_lo;
-          const uint32_t flags = ((qlo / SLOTS) & 1u) | (((qhi / SLOTS) & 1u) << 1) | (p.ok ? RA_F_YOK : 0u) |
-                                 (wlo ? RA_F_WAIT_LO : 0u) | (whi ? RA_F_WAIT_HI : 0u);
-          const int rel0 = i == 0 ? 0 : p.pos_lo, rel1 = i + 1 < P ? next_pos_lo : p.nrows;
-          sts128(d + RA_D_YTAB + 32 * i, slots + row_chunk((uint32_t)p.pos_lo) * a.chunk_bytes,
-                 slots + row_chunk((uint32_t)p.pos_hi) * a.chunk_bytes, full0 + 8 * elo, full0 + 8 * ehi);
-          sts128(d + RA_D_YTAB + 32 * i + 16, flags, __float_as_uint(p.lerp), (seq + rel0) % SLOTS, (uint32_t)(rel1 - rel0));
-          if (p.new_lo) tl::sts32(d + RA_D_ROWS + 4 * p.base, (uint32_t)p.lo);
-          if (p.new_hi) tl::sts32(d + RA_D_ROWS + 4 * (p.base + p.new_lo), (uint32_t)p.hi);
+        } else {
+          if (p.ok) {
+            if (ROWWISE) {
+              // this sample row is completed by (emitted after) row pos_hi; the sample rows completed by one row are consecutive
+              const unsigned grp = __match_any_sync(yvalid, p.pos_hi);
+              if (__ffs(grp) - 1 == lane) tl::sts32(d + RA_D_ETAB + 4 * p.pos_hi, (uint32_t)lane | ((uint32_t)__popc(grp) << 8));
+              tl::sts64(d + RA_D_YTAB + 8 * i, __float_as_uint(p.lerp), p.pos_lo == p.pos_hi ? 1u : 0u);
+            }
+            #pragma unroll
+            for (int w = 0; w < 2; ++w) {
+              if (w == 0 ? p.new_lo : p.new_hi) {
+                const uint32_t j = (uint32_t)(w == 0 ? p.base : p.base + p.new_lo), q = seq + j;
+                if (ROWWISE) sts128(d + RA_D_RTAB + 16 * j, slots + row_chunk(j) * a.chunk_bytes, full0 + 8 * (q % SLOTS), (q / SLOTS) & 1u, 0u);
+                tl::sts32(d + RA_D_ROWS + 4 * j, (uint32_t)(w == 0 ? p.lo : p.hi));
+              }
+            }
+          }
+          if (!ROWWISE && i < P) {
+            // sample-row loop: after sample row i the rows before the next sample row's lo tap are done (at most two:
+            // older ones went with earlier sample rows); out-of-range sample rows hold pos = rows so far
+            (void)prev_ok;
+            const uint32_t qlo = seq + p.pos_lo, qhi = seq + p.pos_hi;
+            const int rel0 = i == 0 ? 0 : p.pos_lo, rel1 = i + 1 < P ? next_pos_lo : p.nrows;
+            const uint32_t ra = rel1 > rel0 ? empty0 + 8 * ((seq + rel0) % SLOTS) : 0u;
+            const uint32_t rb = rel1 > rel0 + 1 ? empty0 + 8 * ((seq + rel0 + 1) % SLOTS) : 0u;
+            sts128(d + RA_D_STAB + 48 * i, slots + row_chunk((uint32_t)p.pos_lo) * a.chunk_bytes,
+                   slots + row_chunk((uint32_t)p.pos_hi) * a.chunk_bytes, full0 + 8 * (qlo % SLOTS), full0 + 8 * (qhi % SLOTS));
+            sts128(d + RA_D_STAB + 48 * i + 16, (qlo / SLOTS) & 1u, (qhi / SLOTS) & 1u, __float_as_uint(p.lerp), (uint32_t)p.ok);
+            tl::sts64(d + RA_D_STAB + 48 * i + 32, ra, rb);
+          }
         }
       }
       __syncwarp();
       if (lane == 0) tl::mbar_arrive(dfull0 + 8 * (n % RA_DESCS));
-      if (kind == RA_KIND_RING) {
+      if (ring) {
         seq += p.nrows;
         const uint32_t last = row_chunk((uint32_t)p.nrows - 1) + k;
         cursor = last == NCH ? 0 : last;
@@ -403,10 +469,11 @@ roialign_nhwc_tma_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaAr
       uint32_t seq = 0, n = 0, cursor = 0, free_chunks = (uint32_t)a.nch, head_row = 0;
       const uint32_t NCH = (uint32_t)a.nch;
       #pragma unroll 1
-      for (int item = blockIdx.x; item < a.total; item += stride, ++n) {
+      for (;; ++n) {
         const uint32_t d = desc0 + (n % RA_DESCS) * RA_D_BYTES;
         tl::mbar_wait(dfull0 + 8 * (n % RA_DESCS), (n / RA_DESCS) & 1);
         const uint4 hdr = tl::lds128(d + RA_D_HDR), is = tl::lds128(d + RA_D_ISSUE);
+        if (hdr.x == RA_KIND_END) break;
         const uint32_t nrows = is.x, k = is.z, bytes = is.w;
         const int x0 = (int)is.y, img = (int)hdr.z;
         const CUtensorMap* tm = &maps.m[hdr.y][k - 1];
@@ -442,13 +509,81 @@ roialign_nhwc_tma_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaAr
   const bool lane_on = lane < cvec;                           // C < 256: the upper lanes have no channels
   uint32_t n = 0;
   #pragma unroll 1
-  for (int item = blockIdx.x; item < a.total; item += stride, ++n) {
+  for (;; ++n) {
     const uint32_t d = desc0 + (n % RA_DESCS) * RA_D_BYTES;
-    __half* o = a.out + (int64_t)item * PP * C;
     tl::mbar_wait(dfull0 + 8 * (n % RA_DESCS), (n / RA_DESCS) & 1);
     const uint4 hdr = tl::lds128(d + RA_D_HDR);
     const int kind = (int)hdr.x;
-    if (kind == RA_KIND_RING) {
+    if (kind == RA_KIND_END) break;
+    const int item = (int)tl::lds32u(d + RA_D_HDR2 + 12);
+    __half* o = a.out + (int64_t)item * PP * C;
+    if (!ROWWISE && kind == RA_KIND_RING_FAST) {
+      // every sample in range, all 32 lanes carry channels: no predicates in the loop
+      uint4 xe[NPX];
+      #pragma unroll
+      for (int k = 0; k < NPX; ++k) {
+        const int px = cw + k * CW;
+        xe[k] = tl::lds128(d + RA_D_XTAB + 16 * (px < P ? px : 0));
+        xe[k].x += (uint32_t)lane * 16u; xe[k].y += (uint32_t)lane * 16u;
+      }
+      uint4* od = reinterpret_cast<uint4*>(o) + (size_t)cw * 32 + lane;           // (py = 0, px = cw)
+      uint32_t e = d + RA_D_STAB;
+      if (NPX == 1) {
+        // one sample column per warp: software-pipelined by hand (the waits and shared-memory loads are volatile asm, the
+        // compiler keeps them in order) -- the taps of sample row py + 1 are fetched before the arithmetic of sample row py
+        uint4 e1 = tl::lds128(e + 16);
+        uint2 e2 = tl::lds64(e + 32);
+        uint4 ta, tb, tc, td;
+        {
+          const uint4 e0 = tl::lds128(e);
+          tl::mbar_wait_nc(e0.z, e1.x);
+          tl::mbar_wait_nc(e0.w, e1.y);
+          ta = tl::lds128(e0.x + xe[0].x); tb = tl::lds128(e0.x + xe[0].y);
+          tc = tl::lds128(e0.y + xe[0].x); td = tl::lds128(e0.y + xe[0].y);
+        }
+        #pragma unroll 1
+        for (int py = 0; py < P; ++py, od += P * 32) {
+          uint4 na = ta, nb = tb, nc = tc, nd = td, n1 = e1;
+          uint2 n2 = e2;
+          if (py + 1 < P) {
+            e += 48;
+            const uint4 n0 = tl::lds128(e);
+            n1 = tl::lds128(e + 16); n2 = tl::lds64(e + 32);
+            tl::mbar_wait_nc(n0.z, n1.x);
+            tl::mbar_wait_nc(n0.w, n1.y);
+            na = tl::lds128(n0.x + xe[0].x); nb = tl::lds128(n0.x + xe[0].y);
+            nc = tl::lds128(n0.y + xe[0].x); nd = tl::lds128(n0.y + xe[0].y);
+          }
+          od[0] = bilerp8p(ta, tb, tc, td, __uint_as_float(xe[0].z), __uint_as_float(e1.z), nz);
+          if (e2.x) {                                         // hand back the rows no later sample row reads
+            __syncwarp();
+            if (lane == 0) { tl::mbar_arrive(e2.x); if (e2.y) tl::mbar_arrive(e2.y); }
+          }
+          ta = na; tb = nb; tc = nc; td = nd; e1 = n1; e2 = n2;
+        }
+      } else {
+        #pragma unroll 1
+        for (int py = 0; py < P; ++py, e += 48, od += P * 32) {
+          const uint4 e0 = tl::lds128(e), e1 = tl::lds128(e + 16);
+          const uint2 e2 = tl::lds64(e + 32);
+          tl::mbar_wait_nc(e0.z, e1.x);
+          tl::mbar_wait_nc(e0.w, e1.y);
+          #pragma unroll
+          for (int k = 0; k < NPX; ++k) {
+            if (cw + k * CW < P) {
+              const uint4 ta = tl::lds128(e0.x + xe[k].x), tb = tl::lds128(e0.x + xe[k].y);
+              const uint4 tc = tl::lds128(e0.y + xe[k].x), td = tl::lds128(e0.y + xe[k].y);
+              od[k * CW * 32] = bilerp8p(ta, tb, tc, td, __uint_as_float(xe[k].z), __uint_as_float(e1.z), nz);
+            }
+          }
+          if (e2.x) {                                           // hand back the rows no later sample row reads
+            __syncwarp();
+            if (lane == 0) { tl::mbar_arrive(e2.x); if (e2.y) tl::mbar_arrive(e2.y); }
+          }
+        }
+      }
+    } else if (!ROWWISE && kind == RA_KIND_RING) {
+      // same loop with the predicates: samples outside the map (zeros), fewer than 256 channels
       uint4 xe[NPX];
       #pragma unroll
       for (int k = 0; k < NPX; ++k) {
@@ -457,32 +592,85 @@ roialign_nhwc_tma_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaAr
         xe[k].x += (uint32_t)lane * 16u; xe[k].y += (uint32_t)lane * 16u;
         if (!lane_on) xe[k].w = 0;
       }
-      uint4* od = reinterpret_cast<uint4*>(o) + (size_t)cw * cvec + lane;       // (py = 0, px = cw)
+      uint4* od = reinterpret_cast<uint4*>(o) + (size_t)cw * cvec + lane;
+      uint32_t e = d + RA_D_STAB;
       #pragma unroll 1
-      for (int py = 0; py < P; ++py) {
-        const uint4 e0 = tl::lds128(d + RA_D_YTAB + 32 * py), e1 = tl::lds128(d + RA_D_YTAB + 32 * py + 16);
-        const float ly = __uint_as_float(e1.y);
-        const bool yok = (e1.x & RA_F_YOK) != 0;
-        if (e1.x & RA_F_WAIT_LO) tl::mbar_wait_nc(e0.z, e1.x & 1u);
-        if (e1.x & RA_F_WAIT_HI) tl::mbar_wait_nc(e0.w, (e1.x >> 1) & 1u);
+      for (int py = 0; py < P; ++py, e += 48, od += (size_t)P * cvec) {
+        const uint4 e0 = tl::lds128(e), e1 = tl::lds128(e + 16);
+        const uint2 e2 = tl::lds64(e + 32);
+        if (e1.w) { tl::mbar_wait_nc(e0.z, e1.x); tl::mbar_wait_nc(e0.w, e1.y); }
         #pragma unroll
         for (int k = 0; k < NPX; ++k) {
           if (cw + k * CW < P && lane_on) {
             uint4 r = z;
-            if (yok && xe[k].w) {
+            if (e1.w && xe[k].w) {
               const uint4 ta = tl::lds128(e0.x + xe[k].x), tb = tl::lds128(e0.x + xe[k].y);
               const uint4 tc = tl::lds128(e0.y + xe[k].x), td = tl::lds128(e0.y + xe[k].y);
-              r = bilerp8p(ta, tb, tc, td, __uint_as_float(xe[k].z), ly, nz);
+              r = bilerp8p(ta, tb, tc, td, __uint_as_float(xe[k].z), __uint_as_float(e1.z), nz);
             }
             od[(size_t)k * CW * cvec] = r;
           }
         }
-        od += (size_t)P * cvec;
-        if (e1.w) {                                           // hand back the rows no later sample row reads
+        if (e2.x) {
           __syncwarp();
-          if (lane == 0)
-            for (uint32_t j = 0; j < e1.w; ++j) tl::mbar_arrive(empty0 + 8 * ((e1.z + j) % SLOTS));
+          if (lane == 0) { tl::mbar_arrive(e2.x); if (e2.y) tl::mbar_arrive(e2.y); }
         }
+      }
+    } else if (kind == RA_KIND_RING) {
+      const uint4 h2 = tl::lds128(d + RA_D_HDR2);
+      const int nrows = (int)hdr.w, lead = (int)h2.y, nvalid = (int)h2.z;
+      uint4 xe[NPX];
+      #pragma unroll
+      for (int k = 0; k < NPX; ++k) {
+        const int px = cw + k * CW;
+        xe[k] = px < P ? tl::lds128(d + RA_D_XTAB + 16 * px) : z;
+        xe[k].x += (uint32_t)lane * 16u; xe[k].y += (uint32_t)lane * 16u;
+        if (!lane_on) xe[k].w = 0;
+      }
+      uint4* const od = reinterpret_cast<uint4*>(o) + (size_t)cw * cvec + lane;     // (py = 0, px = cw)
+      // sample rows outside the map (only possible at the two ends): zeros
+      for (int py = 0; py < P; ++py) {
+        if (py == lead) { py += nvalid; if (py >= P) break; }
+        #pragma unroll
+        for (int k = 0; k < NPX; ++k)
+          if (cw + k * CW < P && lane_on) od[(size_t)py * P * cvec + (size_t)k * CW * cvec] = z;
+      }
+      HRow prev[NPX], cur[NPX];
+      #pragma unroll
+      for (int k = 0; k < NPX; ++k)
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) { prev[k].v[i] = make_float2(0.f, 0.f); cur[k].v[i] = make_float2(0.f, 0.f); }
+      #pragma unroll 1
+      for (int j = 0; j < nrows; ++j) {
+        const uint4 r = tl::lds128(d + RA_D_RTAB + 16 * j);
+        const uint32_t emit = tl::lds32u(d + RA_D_ETAB + 4 * j);
+        tl::mbar_wait_nc(r.y, r.z);
+        #pragma unroll
+        for (int k = 0; k < NPX; ++k)
+          if (xe[k].w) cur[k] = hrow(r.x, xe[k].x, xe[k].y, __uint_as_float(xe[k].z), nz);
+        // the row is in registers: hand its ring space back at once
+        __syncwarp();
+        if (lane == 0) tl::mbar_arrive(empty0 + 8 * ((h2.x + (uint32_t)j) % SLOTS));
+        const int cnt = (int)(emit >> 8), py0 = (int)(emit & 255u);
+        for (int t = 0; t < cnt; ++t) {
+          const uint2 ye = tl::lds64(d + RA_D_YTAB + 8 * (py0 + t));
+          const float ly = __uint_as_float(ye.x);
+          #pragma unroll
+          for (int k = 0; k < NPX; ++k) {
+            if (cw + k * CW < P && lane_on) {
+              uint4 v = z;
+              if (xe[k].w) {
+                HRow top;
+                #pragma unroll
+                for (int i = 0; i < 4; ++i) top.v[i] = ye.y ? cur[k].v[i] : prev[k].v[i];
+                v = ylerp_pack(top, cur[k], ly, nz);
+              }
+              od[(size_t)(py0 + t) * P * cvec + (size_t)k * CW * cvec] = v;
+            }
+          }
+        }
+        #pragma unroll
+        for (int k = 0; k < NPX; ++k) prev[k] = cur[k];
       }
     } else if (kind == RA_KIND_ZERO) {
       for (int e = ct; e < PP * cvec; e += nct) reinterpret_cast<uint4*>(o)[e] = z;
@@ -530,13 +718,13 @@ static int roi_levels(mrcnn_ctx* ctx, int batch, const float* d_rois, int roi_st
   if (total > ctx->roi_cap) {
     MRCNN_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->d_roi_level);
-    MRCNN_CUDA_TRY(ctx, cudaMalloc(&ctx->d_roi_level, sizeof(int32_t) * total));
+    MRCNN_CUDA_TRY(ctx, cudaMalloc(&ctx->d_roi_level, sizeof(int32_t) * (total + 1)));    // + the ticket counter
     ctx->roi_cap = (int)total;
   }
   // PyramidROIAlignLayer.swift:357 ratio = factor / sqrt(W*H)  (Q15: configured size always used)
   double ratio = (double)ctx->cfg.fpn_selection_factor / sqrt((double)ctx->cfg.image_w * (double)ctx->cfg.image_h);
   ProfScope ps(ctx, PROF_GLUE, (double)total * (roi_stride * 4 + 4));
-  roi_level_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(d_rois, roi_stride, total, ratio, ctx->d_roi_level);
+  roi_level_kernel<<<ceil_div(total, 256), 256, 0, ctx->stream>>>(d_rois, roi_stride, total, ratio, ctx->d_roi_level, ctx->d_roi_level + ctx->roi_cap);
   MRCNN_LAUNCH_CHECK(ctx);
   *d_level = ctx->d_roi_level;
   return MRCNN_OK;
@@ -572,9 +760,9 @@ int roialign_chw_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int roi_str
 // ---- host side of the TMA-staged kernel ------------------------------------------------------------------------
 struct RoiTmaEntry {                 // tensor maps of one pyramid (they do not depend on the rois or the pool size)
   const void* p[4]; int hw[8]; int C, batch;
-  RoiTmaMaps maps; int box_px[4][4];
+  RoiTmaMaps maps; int box_px[4][8]; int cpx;
 };
-struct RoiTmaCache { std::vector<RoiTmaEntry> entries; int ctas = 2; int cw = 7; int slot_px = 0; int mode = -1; int ahead = 0; };
+struct RoiTmaCache { std::vector<RoiTmaEntry> entries; int ctas = 2; int rowwise = -1; int slot_px = 0; int mode = -1; int ahead = 0; };
 
 void roialign_release(mrcnn_ctx* ctx) {
   delete (RoiTmaCache*)ctx->roi_tma;
@@ -591,14 +779,15 @@ static int roi_tma_entry(mrcnn_ctx* ctx, RoiTmaCache* cache, int batch, const __
   RoiTmaEntry e;
   for (int l = 0; l < 4; ++l) e.p[l] = d_fmaps[l];
   memcpy(e.hw, hw, sizeof(e.hw)); e.C = C; e.batch = batch;
+  e.cpx = (C % 16 == 0) ? 4 : 8;
   for (int l = 0; l < 4; ++l) {
     const int H = hw[2 * l], W = hw[2 * l + 1];
     // 4-D (C, W, H, N) view of the NHWC map; box = all channels x box_px pixels x one row
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)batch};
     cuuint64_t str[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    for (int wc = 0; wc < 4; ++wc) {
-      const int px = std::min(8 * (wc + 1), W);
+    for (int wc = 0; wc < 8; ++wc) {
+      const int px = std::min(e.cpx * (wc + 1), W);
       e.box_px[l][wc] = px;
       cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)px, 1, 1};
       CUresult r = enc(&e.maps.m[l][wc], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)d_fmaps[l], dims, str, box, es,
@@ -617,14 +806,24 @@ static int roi_tma_entry(mrcnn_ctx* ctx, RoiTmaCache* cache, int batch, const __
   return MRCNN_OK;
 }
 
-template <int PT, int CW, int CTAS>
+template <int PT, int CW, int CTAS, bool ROWWISE>
 static int launch_roialign_tma_t(mrcnn_ctx* ctx, const RoiTmaMaps& maps, RoiTmaArgs a) {
-  auto kern = roialign_nhwc_tma_kernel<PT, CW, CTAS>;
+  auto kern = roialign_nhwc_tma_kernel<PT, CW, CTAS, ROWWISE>;
   constexpr int threads = (CW + 2) * 32;
-  // ring size: what CTAS resident CTAs leave of the SM's shared memory (static part ~6.7 KB + 1 KB reserved per CTA)
-  const int budget = (228 * 1024) / CTAS - 1024 - 7168 - 128;
+  // ring size: what CTAS resident CTAs leave of the SM's shared memory (228 KB per SM; per CTA: the kernel's static
+  // part + 1 KB reserved by the system)
+  static int static_smem = -1;
+  if (static_smem < 0) {
+    cudaFuncAttributes fa;
+    MRCNN_CUDA_TRY(ctx, cudaFuncGetAttributes(&fa, kern));
+    static_smem = (int)fa.sharedSizeBytes;
+  }
+  const int budget = (228 * 1024) / CTAS - 1024 - static_smem - 256;
   a.nch = std::min(budget / a.chunk_bytes, 255);
-  if (a.nch * 8 < a.slot_px * 2) return mrcnn_fail(ctx, MRCNN_EINVAL, "roialign: too many channels for the staged kernel's ring");
+  // the software-pipelined loop holds the rows of two sample rows (4) at once; with the tail skip of the allocator a roi
+  // whose rows take k chunks needs 5k - 1 chunks of ring to make progress: wider rois go the gather way
+  a.slot_px = std::min(a.slot_px, a.cpx * ((a.nch + 1) / 5));
+  if (a.slot_px < a.cpx) return mrcnn_fail(ctx, MRCNN_EINVAL, "roialign: too many channels for the staged kernel's ring");
   const int smem = a.nch * a.chunk_bytes + 128;
   static int per_sm_cached[64] = {0};
   static int smem_cached[64] = {0};
@@ -642,28 +841,19 @@ static int launch_roialign_tma_t(mrcnn_ctx* ctx, const RoiTmaMaps& maps, RoiTmaA
 }
 
 static int launch_roialign_tma(mrcnn_ctx* ctx, RoiTmaCache* cache, const RoiTmaMaps& maps, const RoiTmaArgs& a) {
-  // MRCNN_ROIALIGN_CTAS / MRCNN_ROIALIGN_CW pick the residency and the consumer-warp count (experiments; the defaults
-  // are what measured fastest)
-  const int v = cache->ctas * 10 + cache->cw;
+  // Two consumer loops: by sample row (4 taps per sample; pool 7, where a feature row rarely serves two sample rows) and
+  // by feature row (x-lerp once per row; pool 14, where it usually does).  MRCNN_ROIALIGN_ROWWISE / _CTAS force the other
+  // variant (measurements, tests); the defaults are what measured fastest.
+  const bool roww = cache->rowwise >= 0 ? cache->rowwise != 0 : a.P > 8;
   if (a.P == 7) {
-    switch (v) {
-      case 27: return launch_roialign_tma_t<7, 7, 2>(ctx, maps, a);
-      case 37: return launch_roialign_tma_t<7, 7, 3>(ctx, maps, a);
-      case 24: return launch_roialign_tma_t<7, 4, 2>(ctx, maps, a);
-      case 34: return launch_roialign_tma_t<7, 4, 3>(ctx, maps, a);
-      case 44: return launch_roialign_tma_t<7, 4, 4>(ctx, maps, a);
-    }
-    return launch_roialign_tma_t<7, 7, 2>(ctx, maps, a);
+    if (roww) return launch_roialign_tma_t<7, 7, 2, true>(ctx, maps, a);
+    return cache->ctas == 3 ? launch_roialign_tma_t<7, 7, 3, false>(ctx, maps, a) : launch_roialign_tma_t<7, 7, 2, false>(ctx, maps, a);
   }
   if (a.P == 14) {
-    switch (v) {
-      case 37: return launch_roialign_tma_t<14, 7, 3>(ctx, maps, a);
-      case 24: return launch_roialign_tma_t<14, 4, 2>(ctx, maps, a);   // 4 columns per warp
-      case 34: return launch_roialign_tma_t<14, 4, 3>(ctx, maps, a);
-    }
-    return launch_roialign_tma_t<14, 7, 2>(ctx, maps, a);
+    if (!roww) return launch_roialign_tma_t<14, 7, 2, false>(ctx, maps, a);
+    return cache->ctas == 3 ? launch_roialign_tma_t<14, 7, 3, true>(ctx, maps, a) : launch_roialign_tma_t<14, 7, 2, true>(ctx, maps, a);
   }
-  return launch_roialign_tma_t<0, 7, 2>(ctx, maps, a);
+  return roww ? launch_roialign_tma_t<0, 7, 2, true>(ctx, maps, a) : launch_roialign_tma_t<0, 7, 2, false>(ctx, maps, a);
 }
 
 int roialign_nhwc_f16_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int roi_stride, int64_t R,
@@ -690,8 +880,8 @@ int roialign_nhwc_f16_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int ro
     if (cache->slot_px != 8 && cache->slot_px != 16 && cache->slot_px != 24 && cache->slot_px != 32) cache->slot_px = 32;
     const char* en = getenv("MRCNN_ROIALIGN_CTAS");           // 3: three CTAs per SM with smaller rings
     cache->ctas = en ? std::max(2, std::min(4, atoi(en))) : 2;
-    const char* ew = getenv("MRCNN_ROIALIGN_CW");             // consumer warps per CTA (7 or 4)
-    cache->cw = (ew && atoi(ew) == 4) ? 4 : 7;
+    const char* ew = getenv("MRCNN_ROIALIGN_ROWWISE");        // 0 / 1: force the sample-row / feature-row consumer loop
+    cache->rowwise = ew ? (atoi(ew) != 0) : -1;
     const char* ea = getenv("MRCNN_ROIALIGN_AHEAD");          // rois the producer's L2 prefetch runs ahead (0 = off)
     cache->ahead = ea ? std::max(0, std::min(16, atoi(ea))) : 0;
   }
@@ -705,7 +895,7 @@ int roialign_nhwc_f16_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int ro
     RoiTmaArgs a;
     a.rois = d_rois; a.roi_stride = roi_stride; a.R = (int)R; a.total = (int)(batch * R);
     a.C = (int)C; a.P = P; a.level = lv; a.out = d_out;
-    a.slot_px = cache->slot_px; a.chunk_bytes = 8 * (int)C * 2; a.nch = 0; a.ahead = cache->ahead;
+    a.slot_px = cache->slot_px; a.cpx = e->cpx; a.chunk_bytes = e->cpx * (int)C * 2; a.nch = 0; a.ahead = cache->ahead; a.ticket = ctx->d_roi_level + ctx->roi_cap;
     memcpy(a.box_px, e->box_px, sizeof(a.box_px));
     a.negzero = -0.0f; a.pyr = pyr;
     rc = launch_roialign_tma(ctx, cache, e->maps, a);
