@@ -11,7 +11,7 @@
 // individually so the result is bit-identical to oracle/oracle.c.
 // Every output block is written (fixes Q5: the reference drops the last group).
 //
-//   roialign_nhwc_tma_kernel   the pipeline's kernel: persistent, warp-specialised.  One producer warp stages the
+//   roialign_staged_kernel   the pipeline's kernel: persistent, warp-specialised.  One producer warp stages the
 //                         feature ROWS a roi touches (every distinct tap row once: box = C channels x 8/16/24 pixels x 1
 //                         row, cp.async.bulk.tensor through an 8-slot mbarrier ring) and seven consumer warps compute
 //                         the P x P samples from shared memory, so a row leaves L2 once per roi instead of once per
@@ -202,7 +202,8 @@ struct RoiTmaArgs {
   const float* rois; int roi_stride; int R; int total;      // total = batch * R
   int C, P;
   const int32_t* level;
-  __half* out;
+  void* out;                       // NHWC: __half (R, P, P, C);  CHW: float (R, C, P, P)
+  int pix;                         // bytes from one pixel of a staged row to the next: NHWC C * 2, CHW 4
   int slot_px;                     // widest footprint (pixels) the ring takes (wider rois go the gather way)
   int chunk_bytes;                 // allocation unit of the ring: 8 pixels = 8 * C * 2 bytes (multiple of 128)
   int nch;                         // chunks in the ring
@@ -211,7 +212,8 @@ struct RoiTmaArgs {
   int box_px[4][8];                // pixels a box of [level][class] really holds (min(cpx * (class + 1), W of the level))
   int cpx;                         // pixels per ring chunk: 4 (C % 16 == 0, so that a chunk is a multiple of 128 B) or 8
   float negzero;                   // -0.0f as a runtime value (see tl::mul2)
-  PyramidF16 pyr;
+  PyramidF16 pyr;                  // NHWC maps (sizes are read from here in both layouts)
+  PyramidF32 pyr32;                // CHW maps
 };
 
 // What one lane knows about a roi.  Lanes 0-15 hold y sample `lane`, lanes 16-31 x sample `lane - 16`.
@@ -227,7 +229,7 @@ struct LanePlan {
 // Sample coordinates are non-decreasing in the sample index when a2 >= a1 (fp32 rounding is monotonic), so the taps of
 // sample i satisfy lo(i) >= lo(i-1), hi(i) >= hi(i-1), lo(i) >= hi(i-1) - 1, and out-of-range samples (TF's extrapolation
 // value, 0) can only sit at the two ends.  The distinct rows in ascending order are therefore found with one scan.
-__device__ __forceinline__ LanePlan roi_lane_plan(float y1, float x1, float y2, float x2, int H, int W, int P, int lane, int slot_px) {
+__device__ __forceinline__ LanePlan roi_lane_plan(float y1, float x1, float y2, float x2, int H, int W, int P, int lane, int slot_px, int xalign) {
   const unsigned full = 0xffffffffu;
   LanePlan p;
   const int axis = lane >> 4, i = lane & 15;
@@ -254,7 +256,9 @@ __device__ __forceinline__ LanePlan roi_lane_plan(float y1, float x1, float y2, 
     mn = min(mn, __shfl_xor_sync(full, mn, d, 16));
     mx = max(mx, __shfl_xor_sync(full, mx, d, 16));
   }
-  p.x0 = __shfl_sync(full, mn, 16);
+  // CHW rows start at a multiple of `xalign` pixels: a TMA box whose innermost coordinate is not 16-byte aligned faults
+  // (observed: "illegal instruction"); NHWC rows start at any pixel (the innermost dimension is the channel)
+  p.x0 = __shfl_sync(full, mn, 16) & ~(xalign - 1);
   const int xe = __shfl_sync(full, mx, 16);
   p.nx = xe >= p.x0 ? xe - p.x0 + 1 : 0;
   p.regular = (y2 >= y1) && (x2 >= x1) && P <= 16 && p.nx <= slot_px;
@@ -291,7 +295,8 @@ __device__ __forceinline__ uint4 bilerp8p(uint4 a, uint4 b, uint4 c, uint4 d, fl
 #define RA_D_ISSUE 1072       // 16 B for the issuing warp: rows to stage, leftmost column, chunks per row, row bytes
 #define RA_D_ROWS 1088        // 32 x 4 B: the distinct tap rows (feature-map row indices)
 #define RA_D_ETAB 1216       // 32 x 4 B per distinct row: sample rows COMPLETED by this row (their hi tap): first | count << 8
-#define RA_D_BYTES 1344
+#define RA_D_EXT 1344         // 16 B: CHW layout: bytes from one channel of a staged row to the next (box pixels * 4)
+#define RA_D_BYTES 1360
 #define RA_KIND_ZERO 0        // padding roi (or nothing in range): the block is zeros
 #define RA_KIND_RING 1        // rows staged through the ring
 #define RA_KIND_GATHER 2      // the ring cannot hold this roi: taps straight from global memory
@@ -343,9 +348,9 @@ __device__ __forceinline__ uint4 ylerp_pack(const HRow& top, const HRow& bot, fl
 // fixed slots -- the kernel's speed is set by the bytes it keeps in flight.
 // The loop over sample rows stays rolled on purpose: an unrolled variant (4096 instructions) was instruction-fetch
 // bound (ncu: stall_no_inst on top), see DESIGN.md.
-template <int PT, int CW, int CTAS, bool ROWWISE>
+template <int PT, int CW, int CTAS, bool ROWWISE, bool CHW>
 __global__ void __launch_bounds__((CW + 2) * 32, CTAS)
-roialign_nhwc_tma_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaArgs a) {
+roialign_staged_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaArgs a) {
   constexpr int SLOTS = RA_ROWS;
   extern __shared__ uint8_t ra_smem[];
   __shared__ __align__(8) uint64_t s_full[SLOTS], s_empty[SLOTS], s_dfull[RA_DESCS], s_dempty[RA_DESCS];
@@ -365,7 +370,7 @@ roialign_nhwc_tma_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaAr
   }
   __syncthreads();
   const int C = a.C, P = PT ? PT : a.P, PP = P * P, cvec = C >> 3;
-  const uint32_t pix = (uint32_t)C * 2u;
+  const uint32_t pix = (uint32_t)a.pix;
 
   if (warp == 0) {
     // ---------------- planner: roi -> plan -> descriptor (runs up to RA_DESCS - 1 rois ahead) ----------------
@@ -389,11 +394,11 @@ roialign_nhwc_tma_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaAr
       const int lv = __ldg(a.level + item);
       const float y1 = __ldg(rr), x1 = __ldg(rr + 1), y2 = __ldg(rr + 2), x2 = __ldg(rr + 3);
       const int m = lv >= 0 ? lv - 2 : 0;
-      LanePlan p = roi_lane_plan(y1, x1, y2, x2, a.pyr.h[m], a.pyr.w[m], P, lane, a.slot_px);
+      LanePlan p = roi_lane_plan(y1, x1, y2, x2, a.pyr.h[m], a.pyr.w[m], P, lane, a.slot_px, CHW ? 4 : 1);
       const unsigned allok = __ballot_sync(0xffffffffu, (lane & 15) >= P || p.ok);
       int kind = lv < 0 ? RA_KIND_ZERO : (!p.regular ? RA_KIND_GATHER : ((p.nrows == 0 || p.nx == 0) ? RA_KIND_ZERO : RA_KIND_RING));
       const bool ring = kind == RA_KIND_RING;
-      if (!ROWWISE && ring && allok == 0xffffffffu && cvec == 32) kind = RA_KIND_RING_FAST;
+      if (!ROWWISE && !CHW && ring && allok == 0xffffffffu && cvec == 32) kind = RA_KIND_RING_FAST;
       // chunks per row of this roi, and where row j of the roi lands: rows are placed one after the other from the
       // cursor; a row that would cross the end of the ring starts at chunk 0 instead
       const uint32_t k = ring ? (uint32_t)((p.nx + a.cpx - 1) / a.cpx) : 1u;
@@ -411,7 +416,8 @@ roialign_nhwc_tma_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaAr
         sts128(d + RA_D_HDR, (uint32_t)kind, (uint32_t)m, (uint32_t)img, ring ? (uint32_t)p.nrows : 0u);
         sts128(d + RA_D_HDR + 16, __float_as_uint(y1), __float_as_uint(x1), __float_as_uint(y2), __float_as_uint(x2));
         sts128(d + RA_D_HDR2, seq % SLOTS, yvalid ? (uint32_t)(__ffs(yvalid) - 1) : (uint32_t)P, (uint32_t)__popc(yvalid), (uint32_t)item);
-        sts128(d + RA_D_ISSUE, ring ? (uint32_t)p.nrows : 0u, (uint32_t)p.x0, k, (uint32_t)a.box_px[m][k - 1] * pix);
+        sts128(d + RA_D_ISSUE, ring ? (uint32_t)p.nrows : 0u, (uint32_t)p.x0, k, (uint32_t)a.box_px[m][k - 1] * (uint32_t)(a.chunk_bytes / a.cpx));
+        if (CHW) tl::sts32(d + RA_D_EXT, (uint32_t)a.box_px[m][k - 1] * 4u);
       }
       if (ring) {
         const int i = lane & 15;
@@ -493,7 +499,8 @@ roialign_nhwc_tma_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaAr
           s_chunks_of[e] = (uint8_t)need;
           const int row = (int)tl::lds32u(d + RA_D_ROWS + 4 * j);
           tl::mbar_expect_tx(full0 + 8 * e, bytes);
-          tl::tma_load_4d(slots + c * a.chunk_bytes, tm, full0 + 8 * e, 0, x0, row, img);
+          if (CHW) tl::tma_load_4d(slots + c * a.chunk_bytes, tm, full0 + 8 * e, x0, row, 0, img);     // (W, H, C, N)
+          else tl::tma_load_4d(slots + c * a.chunk_bytes, tm, full0 + 8 * e, 0, x0, row, img);          // (C, W, H, N)
           ++seq;
         }
         tl::mbar_arrive(dempty0 + 8 * (n % RA_DESCS));
@@ -516,7 +523,76 @@ roialign_nhwc_tma_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaAr
     const int kind = (int)hdr.x;
     if (kind == RA_KIND_END) break;
     const int item = (int)tl::lds32u(d + RA_D_HDR2 + 12);
-    __half* o = a.out + (int64_t)item * PP * C;
+    if (CHW) {
+      // ---- boundary layout: staged rows are [channel][pixel] fp32, the output block is (C, P, P) fp32.  A lane owns one
+      // (channel of a group of four, sample column) pair: lanes 8 cs + px; the warp walks the channel groups.
+      float* ob = reinterpret_cast<float*>(a.out) + (int64_t)item * C * PP;
+      if (kind == RA_KIND_RING) {
+        const uint32_t pitch = tl::lds32u(d + RA_D_EXT);
+        const int cs = lane >> 3, pxl = lane & 7;
+        constexpr int NQ = PT ? (PT + 7) / 8 : 2;
+        uint4 xq[NQ];
+        #pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int px = pxl + 8 * q;
+          xq[q] = px < P ? tl::lds128(d + RA_D_XTAB + 16 * px) : z;
+        }
+        uint32_t e = d + RA_D_STAB;
+        #pragma unroll 1
+        for (int py = 0; py < P; ++py, e += 48) {
+          const uint4 e0 = tl::lds128(e), e1 = tl::lds128(e + 16);
+          const uint2 e2 = tl::lds64(e + 32);
+          if (e1.w) { tl::mbar_wait_nc(e0.z, e1.x); tl::mbar_wait_nc(e0.w, e1.y); }
+          const float ly = __uint_as_float(e1.z);
+          #pragma unroll 2
+          for (int g = cw; 4 * g < C; g += CW) {
+            const int c = 4 * g + cs;
+            if (c < C) {
+              const uint32_t lo = e0.x + (uint32_t)c * pitch, hi = e0.y + (uint32_t)c * pitch;
+              #pragma unroll
+              for (int q = 0; q < NQ; ++q) {
+                const int px = pxl + 8 * q;
+                if (px < P) {
+                  float v = 0.0f;
+                  if (e1.w && xq[q].w)
+                    v = bilerp(tl::lds32(lo + xq[q].x), tl::lds32(lo + xq[q].y), tl::lds32(hi + xq[q].x), tl::lds32(hi + xq[q].y),
+                               __uint_as_float(xq[q].z), ly);
+                  ob[((size_t)c * P + py) * P + px] = v;
+                }
+              }
+            }
+          }
+          if (e2.x) {
+            __syncwarp();
+            if (lane == 0) { tl::mbar_arrive(e2.x); if (e2.y) tl::mbar_arrive(e2.y); }
+          }
+        }
+      } else if (kind == RA_KIND_ZERO) {
+        for (int el = ct; el < C * PP; el += nct) ob[el] = 0.0f;
+      } else {
+        // gather path: every element from global memory, like roialign_chw_kernel
+        const uint4 box = tl::lds128(d + RA_D_HDR + 16);
+        const int m = (int)hdr.y;
+        const int H = a.pyr.h[m], W = a.pyr.w[m];
+        const float* fm = a.pyr32.p[m] + (size_t)hdr.z * C * H * W;
+        const float y1 = __uint_as_float(box.x), x1 = __uint_as_float(box.y), y2 = __uint_as_float(box.z), x2 = __uint_as_float(box.w);
+        for (int el = ct; el < C * PP; el += nct) {
+          const int c = el / PP, rem = el - c * PP, py = rem / P, px = rem - py * P;
+          const SampleAxis sy = sample_axis(y1, y2, H, P, py), sx = sample_axis(x1, x2, W, P, px);
+          float v = 0.0f;
+          if (sy.ok && sx.ok) {
+            const float* pl = fm + (size_t)c * H * W;
+            v = bilerp(__ldg(pl + (size_t)sy.lo * W + sx.lo), __ldg(pl + (size_t)sy.lo * W + sx.hi),
+                       __ldg(pl + (size_t)sy.hi * W + sx.lo), __ldg(pl + (size_t)sy.hi * W + sx.hi), sx.lerp, sy.lerp);
+          }
+          ob[el] = v;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) tl::mbar_arrive(dempty0 + 8 * (n % RA_DESCS));
+      continue;
+    }
+    __half* o = reinterpret_cast<__half*>(a.out) + (int64_t)item * PP * C;
     if (!ROWWISE && kind == RA_KIND_RING_FAST) {
       // every sample in range, all 32 lanes carry channels: no predicates in the loop
       uint4 xe[NPX];
@@ -730,36 +806,9 @@ static int roi_levels(mrcnn_ctx* ctx, int batch, const float* d_rois, int roi_st
   return MRCNN_OK;
 }
 
-int roialign_chw_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int roi_stride, int64_t R,
-                     const float* const d_fmaps[4], const int32_t hw[8], int64_t C, int P,
-                     float* d_out, int32_t* d_level_out) {
-  MRCNN_REQUIRE(ctx, batch >= 1 && R >= 1 && R <= 65535, "roialign: bad batch / num_rois");
-  MRCNN_REQUIRE(ctx, roi_stride >= 4, "roialign: roi_row_stride must be >= 4");
-  MRCNN_REQUIRE(ctx, C >= 1 && P >= 1 && P <= 64, "roialign: bad channels / pool");
-  int32_t* lv = nullptr;
-  int rc = roi_levels(ctx, batch, d_rois, roi_stride, R, &lv);
-  if (rc) return rc;
-  PyramidF32 pyr;
-  for (int l = 0; l < 4; ++l) {
-    pyr.p[l] = d_fmaps[l]; pyr.h[l] = hw[2 * l]; pyr.w[l] = hw[2 * l + 1];
-    MRCNN_REQUIRE(ctx, pyr.h[l] >= 1 && pyr.w[l] >= 1, "roialign: bad feature map size");
-  }
-  const int blk = (int)C * P * P;
-  dim3 grid(ceil_div(blk, 1024), (unsigned)R, batch);
-  double map_bytes = 0;
-  for (int l = 0; l < 4; ++l) map_bytes += 4.0 * (double)C * pyr.h[l] * pyr.w[l];
-  // compulsory traffic: every level read once + output written once + rois
-  ProfScope ps(ctx, PROF_ROIALIGN, (double)batch * (map_bytes + 4.0 * R * blk + 4.0 * R * roi_stride));
-  roialign_chw_kernel<<<grid, 256, 0, ctx->stream>>>(d_rois, roi_stride, (int)R, pyr, (int)C, P, lv, d_out);
-  MRCNN_LAUNCH_CHECK(ctx);
-  if (d_level_out)
-    MRCNN_CUDA_TRY(ctx, cudaMemcpyAsync(d_level_out, lv, sizeof(int32_t) * batch * R, cudaMemcpyDeviceToDevice, ctx->stream));
-  return MRCNN_OK;
-}
-
 // ---- host side of the TMA-staged kernel ------------------------------------------------------------------------
 struct RoiTmaEntry {                 // tensor maps of one pyramid (they do not depend on the rois or the pool size)
-  const void* p[4]; int hw[8]; int C, batch;
+  const void* p[4]; int hw[8]; int C, batch; bool chw;
   RoiTmaMaps maps; int box_px[4][8]; int cpx;
 };
 struct RoiTmaCache { std::vector<RoiTmaEntry> entries; int ctas = 2; int rowwise = -1; int slot_px = 0; int mode = -1; int ahead = 0; };
@@ -769,28 +818,53 @@ void roialign_release(mrcnn_ctx* ctx) {
   ctx->roi_tma = nullptr;
 }
 
-static int roi_tma_entry(mrcnn_ctx* ctx, RoiTmaCache* cache, int batch, const __half* const d_fmaps[4],
-                         const int32_t hw[8], int C, const RoiTmaEntry** out) {
+static RoiTmaCache* roi_cache(mrcnn_ctx* ctx) {
+  if (!ctx->roi_tma) ctx->roi_tma = new RoiTmaCache();
+  RoiTmaCache* cache = (RoiTmaCache*)ctx->roi_tma;
+  if (cache->mode < 0) {                                      // knobs for A/B measurements and tests, read once per context
+    const char* e = getenv("MRCNN_ROIALIGN");                 // "gather": the pure gather kernels
+    cache->mode = (e && !strcmp(e, "gather")) ? 0 : 1;
+    const char* es = getenv("MRCNN_ROIALIGN_SLOT_PX");        // widest footprint (pixels) the ring takes: 8, 16, 24 or 32
+    cache->slot_px = es ? atoi(es) : 32;
+    if (cache->slot_px != 8 && cache->slot_px != 16 && cache->slot_px != 24 && cache->slot_px != 32) cache->slot_px = 32;
+    const char* en = getenv("MRCNN_ROIALIGN_CTAS");           // 3: three CTAs per SM with smaller rings
+    cache->ctas = en ? std::max(2, std::min(4, atoi(en))) : 2;
+    const char* ew = getenv("MRCNN_ROIALIGN_ROWWISE");        // 0 / 1: force the sample-row / feature-row consumer loop
+    cache->rowwise = ew ? (atoi(ew) != 0) : -1;
+    const char* ea = getenv("MRCNN_ROIALIGN_AHEAD");          // 1: the planner asks L2 for a roi's rows when it plans it
+    cache->ahead = ea ? std::max(0, std::min(16, atoi(ea))) : 0;
+  }
+  return cache;
+}
+
+static int roi_tma_entry(mrcnn_ctx* ctx, RoiTmaCache* cache, int batch, const void* const d_fmaps[4],
+                         const int32_t hw[8], int C, bool chw, const RoiTmaEntry** out) {
   for (const auto& e : cache->entries)
-    if (e.C == C && e.batch == batch && !memcmp(e.hw, hw, sizeof(e.hw)) && e.p[0] == d_fmaps[0] && e.p[1] == d_fmaps[1] &&
+    if (e.C == C && e.batch == batch && e.chw == chw && !memcmp(e.hw, hw, sizeof(e.hw)) && e.p[0] == d_fmaps[0] && e.p[1] == d_fmaps[1] &&
         e.p[2] == d_fmaps[2] && e.p[3] == d_fmaps[3]) { *out = &e; return MRCNN_OK; }
   PFN_tmapEncodeTiled enc = tmap_encode_fn();
   if (!enc) return mrcnn_fail(ctx, MRCNN_ECUDA, "roialign: cuTensorMapEncodeTiled not available from the driver");
   RoiTmaEntry e;
   for (int l = 0; l < 4; ++l) e.p[l] = d_fmaps[l];
-  memcpy(e.hw, hw, sizeof(e.hw)); e.C = C; e.batch = batch;
-  e.cpx = (C % 16 == 0) ? 4 : 8;
+  memcpy(e.hw, hw, sizeof(e.hw)); e.C = C; e.batch = batch; e.chw = chw;
+  e.cpx = (chw || C % 16 == 0) ? 4 : 8;
   for (int l = 0; l < 4; ++l) {
     const int H = hw[2 * l], W = hw[2 * l + 1];
-    // 4-D (C, W, H, N) view of the NHWC map; box = all channels x box_px pixels x one row
+    // NHWC: 4-D (C, W, H, N) view, box = all channels x box_px pixels x one row.
+    // CHW:  4-D (W, H, C, N) view, box = box_px pixels x one row x all channels (lands as [channel][pixel]).
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)batch};
     cuuint64_t str[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+    if (chw) {
+      dims[0] = (cuuint64_t)W; dims[1] = (cuuint64_t)H; dims[2] = (cuuint64_t)C;
+      str[0] = (cuuint64_t)W * 4; str[1] = (cuuint64_t)W * 4 * H; str[2] = (cuuint64_t)W * 4 * H * C;
+    }
     cuuint32_t es[4] = {1, 1, 1, 1};
     for (int wc = 0; wc < 8; ++wc) {
       const int px = std::min(e.cpx * (wc + 1), W);
       e.box_px[l][wc] = px;
       cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)px, 1, 1};
-      CUresult r = enc(&e.maps.m[l][wc], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)d_fmaps[l], dims, str, box, es,
+      if (chw) { box[0] = (cuuint32_t)px; box[1] = 1; box[2] = (cuuint32_t)C; }
+      CUresult r = enc(&e.maps.m[l][wc], chw ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)d_fmaps[l], dims, str, box, es,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) {
@@ -806,9 +880,9 @@ static int roi_tma_entry(mrcnn_ctx* ctx, RoiTmaCache* cache, int batch, const __
   return MRCNN_OK;
 }
 
-template <int PT, int CW, int CTAS, bool ROWWISE>
+template <int PT, int CW, int CTAS, bool ROWWISE, bool CHW = false>
 static int launch_roialign_tma_t(mrcnn_ctx* ctx, const RoiTmaMaps& maps, RoiTmaArgs a) {
-  auto kern = roialign_nhwc_tma_kernel<PT, CW, CTAS, ROWWISE>;
+  auto kern = roialign_staged_kernel<PT, CW, CTAS, ROWWISE, CHW>;
   constexpr int threads = (CW + 2) * 32;
   // ring size: what CTAS resident CTAs leave of the SM's shared memory (228 KB per SM; per CTA: the kernel's static
   // part + 1 KB reserved by the system)
@@ -820,9 +894,10 @@ static int launch_roialign_tma_t(mrcnn_ctx* ctx, const RoiTmaMaps& maps, RoiTmaA
   }
   const int budget = (228 * 1024) / CTAS - 1024 - static_smem - 256;
   a.nch = std::min(budget / a.chunk_bytes, 255);
-  // the software-pipelined loop holds the rows of two sample rows (4) at once; with the tail skip of the allocator a roi
-  // whose rows take k chunks needs 5k - 1 chunks of ring to make progress: wider rois go the gather way
-  a.slot_px = std::min(a.slot_px, a.cpx * ((a.nch + 1) / 5));
+  // the software-pipelined loop holds the rows of two sample rows (4) at once (the others 2); with the tail skip of the
+  // allocator a roi whose rows take k chunks needs 5k - 1 (3k - 1) chunks of ring to make progress: wider rois go the
+  // gather way
+  a.slot_px = std::min(a.slot_px, a.cpx * ((a.nch + 1) / (CHW ? 3 : 5)));
   if (a.slot_px < a.cpx) return mrcnn_fail(ctx, MRCNN_EINVAL, "roialign: too many channels for the staged kernel's ring");
   const int smem = a.nch * a.chunk_bytes + 128;
   static int per_sm_cached[64] = {0};
@@ -870,39 +945,73 @@ int roialign_nhwc_f16_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int ro
   if (rc) return rc;
   PyramidF16 pyr;
   for (int l = 0; l < 4; ++l) { pyr.p[l] = d_fmaps[l]; pyr.h[l] = hw[2 * l]; pyr.w[l] = hw[2 * l + 1]; }
-  if (!ctx->roi_tma) ctx->roi_tma = new RoiTmaCache();
-  RoiTmaCache* cache = (RoiTmaCache*)ctx->roi_tma;
-  if (cache->mode < 0) {
-    const char* e = getenv("MRCNN_ROIALIGN");                 // "gather": the pure gather kernel (A/B measurements, tests)
-    cache->mode = (e && !strcmp(e, "gather")) ? 0 : 1;
-    const char* es = getenv("MRCNN_ROIALIGN_SLOT_PX");        // ring slot width in pixels (8, 16, 24 or 32)
-    cache->slot_px = es ? atoi(es) : 32;
-    if (cache->slot_px != 8 && cache->slot_px != 16 && cache->slot_px != 24 && cache->slot_px != 32) cache->slot_px = 32;
-    const char* en = getenv("MRCNN_ROIALIGN_CTAS");           // 3: three CTAs per SM with smaller rings
-    cache->ctas = en ? std::max(2, std::min(4, atoi(en))) : 2;
-    const char* ew = getenv("MRCNN_ROIALIGN_ROWWISE");        // 0 / 1: force the sample-row / feature-row consumer loop
-    cache->rowwise = ew ? (atoi(ew) != 0) : -1;
-    const char* ea = getenv("MRCNN_ROIALIGN_AHEAD");          // rois the producer's L2 prefetch runs ahead (0 = off)
-    cache->ahead = ea ? std::max(0, std::min(16, atoi(ea))) : 0;
-  }
+  RoiTmaCache* cache = roi_cache(ctx);
   // bytes this launch has to move at least: the output once + the rois; the map bytes the rois really touch are
   // data dependent (bench.py reports them from the roi footprints and, under ncu, from dram__bytes)
   ProfScope ps(ctx, PROF_ROIALIGN, (double)batch * (2.0 * R * C * P * P + 4.0 * R * roi_stride));
-  if (cache->mode == 1 && C <= 256 && (((uintptr_t)d_fmaps[0] | (uintptr_t)d_fmaps[1] | (uintptr_t)d_fmaps[2] | (uintptr_t)d_fmaps[3]) & 15) == 0) {
+  if (cache->mode == 1 && C <= 256 && P <= 16 && (((uintptr_t)d_fmaps[0] | (uintptr_t)d_fmaps[1] | (uintptr_t)d_fmaps[2] | (uintptr_t)d_fmaps[3]) & 15) == 0) {
     const RoiTmaEntry* e = nullptr;
-    rc = roi_tma_entry(ctx, cache, batch, d_fmaps, hw, (int)C, &e);
+    rc = roi_tma_entry(ctx, cache, batch, (const void* const*)d_fmaps, hw, (int)C, false, &e);
     if (rc) return rc;
     RoiTmaArgs a;
     a.rois = d_rois; a.roi_stride = roi_stride; a.R = (int)R; a.total = (int)(batch * R);
     a.C = (int)C; a.P = P; a.level = lv; a.out = d_out;
-    a.slot_px = cache->slot_px; a.cpx = e->cpx; a.chunk_bytes = e->cpx * (int)C * 2; a.nch = 0; a.ahead = cache->ahead; a.ticket = ctx->d_roi_level + ctx->roi_cap;
+    a.pix = (int)C * 2; a.slot_px = cache->slot_px; a.cpx = e->cpx; a.chunk_bytes = e->cpx * (int)C * 2; a.nch = 0; a.ahead = cache->ahead; a.ticket = ctx->d_roi_level + ctx->roi_cap;
     memcpy(a.box_px, e->box_px, sizeof(a.box_px));
-    a.negzero = -0.0f; a.pyr = pyr;
+    a.negzero = -0.0f; a.pyr = pyr; memset(&a.pyr32, 0, sizeof(a.pyr32));
     rc = launch_roialign_tma(ctx, cache, e->maps, a);
     if (rc) return rc;
   } else {
     dim3 grid((unsigned)R, batch);
     roialign_nhwc_kernel<<<grid, 256, 0, ctx->stream>>>(d_rois, roi_stride, (int)R, pyr, (int)C, P, lv, d_out);
+  }
+  MRCNN_LAUNCH_CHECK(ctx);
+  if (d_level_out)
+    MRCNN_CUDA_TRY(ctx, cudaMemcpyAsync(d_level_out, lv, sizeof(int32_t) * batch * R, cudaMemcpyDeviceToDevice, ctx->stream));
+  return MRCNN_OK;
+}
+
+int roialign_chw_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int roi_stride, int64_t R,
+                     const float* const d_fmaps[4], const int32_t hw[8], int64_t C, int P,
+                     float* d_out, int32_t* d_level_out) {
+  MRCNN_REQUIRE(ctx, batch >= 1 && R >= 1 && R <= 65535, "roialign: bad batch / num_rois");
+  MRCNN_REQUIRE(ctx, (int64_t)batch * R <= INT_MAX, "roialign: batch * num_rois too large");
+  MRCNN_REQUIRE(ctx, roi_stride >= 4, "roialign: roi_row_stride must be >= 4");
+  MRCNN_REQUIRE(ctx, C >= 1 && P >= 1 && P <= 64, "roialign: bad channels / pool");
+  int32_t* lv = nullptr;
+  int rc = roi_levels(ctx, batch, d_rois, roi_stride, R, &lv);
+  if (rc) return rc;
+  PyramidF32 pyr;
+  bool tma_ok = C <= 256 && (C % 8) == 0 && P <= 16;     // pool > 16: every roi would take the in-kernel gather path
+  for (int l = 0; l < 4; ++l) {
+    pyr.p[l] = d_fmaps[l]; pyr.h[l] = hw[2 * l]; pyr.w[l] = hw[2 * l + 1];
+    MRCNN_REQUIRE(ctx, pyr.h[l] >= 1 && pyr.w[l] >= 1, "roialign: bad feature map size");
+    // TMA needs 16-byte aligned maps and row strides (W * 4 bytes)
+    tma_ok = tma_ok && ((uintptr_t)d_fmaps[l] & 15) == 0 && (pyr.w[l] % 4) == 0;
+  }
+  const int blk = (int)C * P * P;
+  RoiTmaCache* cache = roi_cache(ctx);
+  // bytes this launch has to move at least: the output once + the rois (the touched map bytes are data dependent)
+  ProfScope ps(ctx, PROF_ROIALIGN, (double)batch * (4.0 * R * blk + 4.0 * R * roi_stride));
+  if (cache->mode == 1 && tma_ok) {
+    const RoiTmaEntry* e = nullptr;
+    rc = roi_tma_entry(ctx, cache, batch, (const void* const*)d_fmaps, hw, (int)C, true, &e);
+    if (rc) return rc;
+    RoiTmaArgs a;
+    a.rois = d_rois; a.roi_stride = roi_stride; a.R = (int)R; a.total = (int)(batch * R);
+    a.C = (int)C; a.P = P; a.level = lv; a.out = d_out;
+    a.pix = 4; a.slot_px = cache->slot_px; a.cpx = e->cpx; a.chunk_bytes = e->cpx * 4 * (int)C; a.nch = 0; a.ahead = 0;
+    a.ticket = ctx->d_roi_level + ctx->roi_cap;
+    memcpy(a.box_px, e->box_px, sizeof(a.box_px));
+    a.negzero = -0.0f; a.pyr32 = pyr;
+    for (int l = 0; l < 4; ++l) { a.pyr.p[l] = nullptr; a.pyr.h[l] = pyr.h[l]; a.pyr.w[l] = pyr.w[l]; }
+    if (P == 7) rc = launch_roialign_tma_t<7, 7, 2, false, true>(ctx, e->maps, a);
+    else if (P == 14) rc = launch_roialign_tma_t<14, 7, 2, false, true>(ctx, e->maps, a);
+    else rc = launch_roialign_tma_t<0, 7, 2, false, true>(ctx, e->maps, a);
+    if (rc) return rc;
+  } else {
+    dim3 grid(ceil_div(blk, 1024), (unsigned)R, batch);
+    roialign_chw_kernel<<<grid, 256, 0, ctx->stream>>>(d_rois, roi_stride, (int)R, pyr, (int)C, P, lv, d_out);
   }
   MRCNN_LAUNCH_CHECK(ctx);
   if (d_level_out)

@@ -143,6 +143,136 @@ def test_pyramid_roialign_nhwc_f16(pkg, ctx, orc):
         np.testing.assert_array_equal(out[i].view(np.uint16), o0.view(np.uint16))      # bit-exact fp16
 
 
+@pytest.mark.parametrize("pool,ch", [(7, 256), (14, 64), (7, 32), (3, 40), (16, 32), (20, 16), (7, 12)])
+def test_roialign_boundary_layout_every_path(pkg, ctx, orc, pool, ch):
+    """Boundary (CHW fp32) layout: the staged kernel's ring / gather / padding paths, run-time pool sizes, channel counts
+    TMA boxes cannot cover (12: the plain gather kernel), bit for bit against the oracle."""
+    b, r = 2, 120
+    maps = [np.stack([pkg.synth.feature_maps(90 + i, channels=ch)[l] for i in range(b)]) for l in range(4)]
+    rois = np.stack([_adversarial_rois(pkg, r, 95 + i) for i in range(b)])
+    out = np.full((b, r, ch, pool, pool), 3.0, np.float32)
+    lv = np.zeros((b, r), np.int32)
+    pkg.PyramidROIAlignLayer({"poolSize": pool}, context=ctx).evaluate([rois] + maps, [out], level=lv)
+    for i in range(b):
+        o0, l0 = orc.pyramid_roialign(rois[i], [m[i] for m in maps], pool)
+        np.testing.assert_array_equal(lv[i], l0)
+        np.testing.assert_array_equal(out[i].view(np.uint32), o0.view(np.uint32))
+    assert {-1, 2, 3, 4, 5} <= set(np.unique(lv))
+
+
+def test_roialign_boundary_layout_gather_variant_agrees(pkg, orc, monkeypatch):
+    monkeypatch.setenv("MRCNN_ROIALIGN", "gather")
+    c = pkg.Context()
+    try:
+        b, r, ch, pool = 1, 120, 32, 7
+        maps = [np.stack([pkg.synth.feature_maps(97, channels=ch)[l]]) for l in range(4)]
+        rois = np.stack([_adversarial_rois(pkg, r, 98)])
+        out = np.zeros((b, r, ch, pool, pool), np.float32)
+        pkg.PyramidROIAlignLayer({"poolSize": pool}, context=c).evaluate([rois] + maps, [out])
+        o0, _ = orc.pyramid_roialign(rois[0], [m[0] for m in maps], pool)
+        np.testing.assert_array_equal(out[0].view(np.uint32), o0.view(np.uint32))
+    finally:
+        c.close()
+
+
+def _run_nhwc(pkg, ctx, rois, hwc, pool, stride=4):
+    import ctypes as C
+    import torch
+    b, r = rois.shape[:2]
+    ch = hwc[0].shape[-1]
+    d_maps = [torch.from_numpy(m).cuda() for m in hwc]
+    d_rois = torch.from_numpy(rois).cuda()
+    d_out = torch.full((b, r, pool, pool, ch), 5.0, dtype=torch.float16, device="cuda")
+    d_lv = torch.zeros((b, r), dtype=torch.int32, device="cuda")
+    hw = (C.c_int32 * 8)(*[d for m in hwc for d in m.shape[1:3]])
+    fp = (C.c_void_p * 4)(*[m.data_ptr() for m in d_maps])
+    pkg._cabi.check(ctx.handle, pkg.lib().mrcnn_roialign_nhwc_f16(ctx.handle, b, d_rois.data_ptr(), stride, r, fp, hw, ch, pool,
+                                                               d_out.data_ptr(), d_lv.data_ptr()))
+    ctx.synchronize()
+    return d_out.cpu().numpy(), d_lv.cpu().numpy()
+
+
+def _adversarial_rois(pkg, r, seed):
+    """Random rois plus the cases every branch of the staged kernel (roialign.cu) has to get right: boxes touching the
+    image border (last sample lands on / one ulp beyond the last pixel -> TF's extrapolation value 0), boxes reaching
+    outside [0, 1] (leading / trailing out-of-range samples), inverted boxes (the ring cannot serve them: gather path),
+    boxes wider than a ring slot (level 5, > 32 feature pixels is impossible at 1024^2, so a wide level-2 box via tiny
+    height), degenerate boxes (padding), a sample row exactly on a feature row, tiny boxes (all samples in one pixel)."""
+    rois = pkg.synth.random_rois(r, seed, n_pad=3).copy()
+    rng = np.random.default_rng(seed)
+    special = [
+        [0.0, 0.0, 1.0, 1.0], [0.5, 0.5, 1.0, 1.0], [0.0, 0.0, 0.03, 0.05], [0.9, 0.9, 1.0, 1.0],
+        [0.25, 0.25, 0.25 + 6 / 255.0, 0.25 + 6 / 255.0],            # samples on feature rows of P2
+        [0.3, 0.3, 0.3001, 0.3001],                                     # all samples inside one pixel
+        [-0.1, -0.05, 0.4, 0.5], [0.6, 0.7, 1.2, 1.1], [-0.2, -0.2, 1.3, 1.3],      # outside the map on one / both ends
+        [0.8, 0.6, 0.2, 0.1],                                           # inverted on both axes: valid level, gather path
+        [0.4, 0.1, 0.401, 0.95],                                        # very wide, very flat: level 2, > 32 pixels wide
+        [0.2, 0.2, 0.2, 0.6], [0.2, 0.6, 0.5, 0.2],                     # zero / negative area -> padding
+        [np.nan, 0.1, 0.5, 0.5],
+    ]
+    for k, sp in enumerate(special):
+        rois[2 * k + 1, :4] = sp
+    for k in range(20):                                                  # boxes clipped at 1.0 like ProposalLayer's output
+        y1, x1 = rng.uniform(0.3, 0.95, 2)
+        rois[40 + k, :4] = [y1, x1, 1.0 if k % 2 else min(1.0, y1 + 0.2), 1.0 if k % 3 else min(1.0, x1 + 0.3)]
+    return rois.astype(np.float32)
+
+
+@pytest.mark.parametrize("pool,ch", [(7, 256), (14, 256), (7, 32), (14, 64), (1, 256), (2, 256), (5, 128), (16, 256), (20, 64)])
+def test_roialign_nhwc_f16_every_path(pkg, ctx, orc, pool, ch):
+    """The staged kernel against the oracle, bit for bit, on rois that drive each of its paths: the predicate-free ring
+    loop (pool 7, 256 channels), the generic ring loop (out-of-range samples, fewer channels), the row-wise loop (pool
+    14), run-time pool sizes (1, 2, 5, 16), the gather path (inverted / too wide boxes, pool > 16) and padding blocks."""
+    b, r = 2, 120
+    maps = [np.stack([pkg.synth.feature_maps(30 + i, channels=ch)[l] for i in range(b)]) for l in range(4)]
+    hwc = [np.ascontiguousarray(m.transpose(0, 2, 3, 1)).astype(np.float16) for m in maps]
+    rois = np.stack([_adversarial_rois(pkg, r, 40 + i) for i in range(b)])
+    out, lv = _run_nhwc(pkg, ctx, rois, hwc, pool)
+    for i in range(b):
+        o0, l0 = orc.pyramid_roialign_nhwc_f16(rois[i], [m[i] for m in hwc], pool)
+        np.testing.assert_array_equal(lv[i], l0)
+        np.testing.assert_array_equal(out[i].view(np.uint16), o0.view(np.uint16))
+    assert {-1, 2, 3, 4, 5} <= set(np.unique(lv))
+
+
+@pytest.mark.parametrize("env", [{"MRCNN_ROIALIGN": "gather"}, {"MRCNN_ROIALIGN_ROWWISE": "1"}, {"MRCNN_ROIALIGN_ROWWISE": "0"},
+                                 {"MRCNN_ROIALIGN_CTAS": "3"}, {"MRCNN_ROIALIGN_SLOT_PX": "8"}, {"MRCNN_ROIALIGN_AHEAD": "1"}])
+def test_roialign_nhwc_f16_kernel_variants_agree(pkg, orc, env, monkeypatch):
+    """Every variant of the kernel (pure gather, either consumer loop for either pool size, three CTAs per SM, narrow ring
+    slots = most rois on the gather path, L2 prefetch) gives the oracle's bits.  The knobs are read once per context."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    c = pkg.Context()
+    try:
+        b, r, ch = 2, 120, 256
+        maps = [np.stack([pkg.synth.feature_maps(50 + i, channels=ch)[l] for i in range(b)]) for l in range(4)]
+        hwc = [np.ascontiguousarray(m.transpose(0, 2, 3, 1)).astype(np.float16) for m in maps]
+        rois = np.stack([_adversarial_rois(pkg, r, 60 + i) for i in range(b)])
+        for pool in (7, 14):
+            out, lv = _run_nhwc(pkg, c, rois, hwc, pool)
+            for i in range(b):
+                o0, l0 = orc.pyramid_roialign_nhwc_f16(rois[i], [m[i] for m in hwc], pool)
+                np.testing.assert_array_equal(lv[i], l0)
+                np.testing.assert_array_equal(out[i].view(np.uint16), o0.view(np.uint16))
+    finally:
+        c.close()
+
+
+def test_roialign_nhwc_f16_many_rois_per_cta(pkg, ctx, orc):
+    """More rois than the persistent grid has CTAs (2 x 148): descriptors and ring entries wrap many times, rois are
+    handed out by the ticket counter; repeated launches re-arm it."""
+    b, r, ch, pool = 3, 1000, 256, 7
+    maps = [np.stack([pkg.synth.feature_maps(70 + i, channels=ch)[l] for i in range(b)]) for l in range(4)]
+    hwc = [np.ascontiguousarray(m.transpose(0, 2, 3, 1)).astype(np.float16) for m in maps]
+    rois = np.stack([pkg.synth.random_rois(r, 80 + i, n_pad=11) for i in range(b)])
+    for _ in range(2):
+        out, lv = _run_nhwc(pkg, ctx, rois, hwc, pool)
+    for i in range(b):
+        o0, l0 = orc.pyramid_roialign_nhwc_f16(rois[i], [m[i] for m in hwc], pool)
+        np.testing.assert_array_equal(lv[i], l0)
+        np.testing.assert_array_equal(out[i].view(np.uint16), o0.view(np.uint16))
+
+
 def test_classifier_select(pkg, ctx, orc):
     probs = np.stack([pkg.synth.classifier_outputs(500, i)[0] for i in range(2)])
     bbox = np.stack([pkg.synth.classifier_outputs(500, i)[1] for i in range(2)])

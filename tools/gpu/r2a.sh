@@ -8,7 +8,7 @@ echo "== microbench staged"; timeout 300 python tools/bench_roialign.py --case "
 echo "== microbench staged slot 32"; MRCNN_ROIALIGN_SLOT_PX=32 timeout 300 python tools/bench_roialign.py --case "$CASES" --out gpurun_out/ra_staged32.json 2>&1 | tail -6
 echo "== microbench gather"; MRCNN_ROIALIGN=gather timeout 300 python tools/bench_roialign.py --case "$CASES" --out gpurun_out/ra_gather.json 2>&1 | tail -6
 echo "== ncu staged b8 R1000 P7"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:roialign_nhwc_tma -s 3 -c 1 -o gpurun_out/r2a_roialign_tma -f \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:roialign_staged -s 3 -c 1 -o gpurun_out/r2a_roialign_tma -f \
   python tools/bench_roialign.py --case "nhwc_f16,8,1000,7" --iters 3 --out gpurun_out/ra_ncu.json > gpurun_out/ncu_r2a.log 2>&1; tail -2 gpurun_out/ncu_r2a.log
 echo "== pipeline bench (staged roialign)"; timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r2a.json 2> gpurun_out/bench_r2a.err; tail -2 gpurun_out/bench_r2a.err
 python - <<'PY'

@@ -7,5 +7,5 @@ echo "== microbench staged 8 slots x 2 CTAs"; timeout 300 python tools/bench_roi
 echo "== microbench staged 5 slots x 3 CTAs"; MRCNN_ROIALIGN_SLOTS=5 timeout 300 python tools/bench_roialign.py --case "$CASES" --out gpurun_out/rb_staged5.json 2>&1 | tail -6
 echo "== microbench staged 16 px slots"; MRCNN_ROIALIGN_SLOT_PX=16 timeout 300 python tools/bench_roialign.py --case "$CASES" --out gpurun_out/rb_staged16.json 2>&1 | tail -6
 echo "== ncu staged b8 R1000 P7"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:roialign_nhwc_tma -s 3 -c 1 -o gpurun_out/r2b_roialign_tma -f \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:roialign_staged -s 3 -c 1 -o gpurun_out/r2b_roialign_tma -f \
   python tools/bench_roialign.py --case "nhwc_f16,8,1000,7" --iters 3 --out gpurun_out/rb_ncu.json > gpurun_out/ncu_r2b.log 2>&1; tail -2 gpurun_out/ncu_r2b.log

@@ -6,5 +6,5 @@ for v in "AHEAD=0" "AHEAD=2" "AHEAD=4" "AHEAD=8" "AHEAD=2 MRCNN_ROIALIGN_SLOTS=5
   echo "== microbench staged $v"; env MRCNN_ROIALIGN_$v timeout 300 python tools/bench_roialign.py --case "$CASES" --out gpurun_out/rc.json 2>&1 | tail -4
 done
 echo "== ncu staged b8 R1000 P7 (ahead 2)"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:roialign_nhwc_tma -s 3 -c 1 -o gpurun_out/r2c_roialign_tma -f \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:roialign_staged -s 3 -c 1 -o gpurun_out/r2c_roialign_tma -f \
   python tools/bench_roialign.py --case "nhwc_f16,8,1000,7" --iters 3 --out gpurun_out/rc_ncu.json > gpurun_out/ncu_r2c.log 2>&1; tail -2 gpurun_out/ncu_r2c.log

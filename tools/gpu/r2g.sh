@@ -9,5 +9,5 @@ for v in "CTAS=2" "CTAS=3" "ROWWISE=0" "ROWWISE=1"; do
   echo "== microbench staged $v"; env MRCNN_ROIALIGN_$v timeout 300 python tools/bench_roialign.py --case "$CASES" --out gpurun_out/rg.json 2>&1 | tail -4
 done
 echo "== ncu staged b8 R1000 P7 default"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:roialign_nhwc_tma -s 3 -c 1 -o gpurun_out/r2g_roialign_tma -f \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:roialign_staged -s 3 -c 1 -o gpurun_out/r2g_roialign_tma -f \
   python tools/bench_roialign.py --case "nhwc_f16,8,1000,7" --iters 3 --out gpurun_out/rg_ncu.json > gpurun_out/ncu_r2g.log 2>&1; tail -2 gpurun_out/ncu_r2g.log
