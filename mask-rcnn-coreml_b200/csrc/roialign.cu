@@ -45,6 +45,45 @@ __global__ void roi_level_kernel(const float* __restrict__ rois, int roi_stride,
   level[i] = lv;
 }
 
+// Processing order of the staged kernel: per image, rois sorted by (level, y centre, x centre), so that the ~300 rois
+// in flight at any time read one band of one map and overlapping rois hit in L2 (the reference groups its rois by
+// level for the same reason, PyramidROIAlignLayer.swift:432-466; the OUTPUT stays in roi order).  One CTA per image,
+// bitonic sort of (key << 32 | roi) in shared memory; n = power of two >= R, at most 4096.
+__global__ void __launch_bounds__(1024)
+roi_order_kernel(const float* __restrict__ rois, int roi_stride, int R, int n, const int32_t* __restrict__ level,
+                 int32_t* __restrict__ order) {
+  extern __shared__ unsigned long long so_keys[];
+  const int img = blockIdx.x;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    unsigned long long k = ~0ull;
+    if (i < R) {
+      const int64_t gi = (int64_t)img * R + i;
+      const float* r = rois + gi * roi_stride;
+      const int lv = level[gi];
+      const float yc = 0.5f * (r[0] + r[2]), xc = 0.5f * (r[1] + r[3]);
+      const unsigned yq = min(4095u, (unsigned)(fminf(fmaxf(yc, 0.0f), 1.0f) * 4096.0f));     // NaN -> 0
+      const unsigned xq = min(4095u, (unsigned)(fminf(fmaxf(xc, 0.0f), 1.0f) * 4096.0f));
+      const unsigned key = ((unsigned)(lv < 0 ? 7 : lv) << 24) | ((yq & 4095u) << 12) | (xq & 4095u);
+      k = ((unsigned long long)key << 32) | (unsigned)i;
+    }
+    so_keys[i] = k;
+  }
+  __syncthreads();
+  for (int size = 2; size <= n; size <<= 1)
+    for (int st = size >> 1; st > 0; st >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int j = i ^ st;
+        if (j > i) {
+          const unsigned long long a = so_keys[i], b = so_keys[j];
+          const bool up = (i & size) == 0;
+          if ((a > b) == up) { so_keys[i] = b; so_keys[j] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < R; i += blockDim.x) order[(int64_t)img * R + i] = img * R + (int)(so_keys[i] & 0xffffffffu);
+}
+
 struct PyramidF32 { const float* p[4]; int h[4]; int w[4]; };
 struct PyramidF16 { const __half* p[4]; int h[4]; int w[4]; };
 
@@ -209,6 +248,7 @@ struct RoiTmaArgs {
   int nch;                         // chunks in the ring
   int ahead;                       // 1: the planner asks L2 for a roi's rows when it plans it (0: off)
   int* ticket;                     // work counter, zeroed by the level kernel: rois are handed out in order, one at a time
+  const int32_t* order;            // processing order (roi_order_kernel) or nullptr = roi order
   int box_px[4][8];                // pixels a box of [level][class] really holds (min(cpx * (class + 1), W of the level))
   int cpx;                         // pixels per ring chunk: 4 (C % 16 == 0, so that a chunk is a multiple of 128 B) or 8
   float negzero;                   // -0.0f as a runtime value (see tl::mul2)
@@ -383,6 +423,7 @@ roialign_staged_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaArgs
       // next roi: a ticket (rois in order; CTAs that drew cheap rois simply draw more of them -- no tail of unlucky CTAs)
       int item = 0;
       if (lane == 0) item = atomicAdd(a.ticket, 1);
+      if (lane == 0 && item < a.total && a.order) item = __ldg(a.order + item);
       item = __shfl_sync(0xffffffffu, item, 0);
       const uint32_t d = desc0 + (n % RA_DESCS) * RA_D_BYTES;
       if (item >= a.total) {
@@ -557,7 +598,10 @@ roialign_staged_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaArgs
                   if (e1.w && xq[q].w)
                     v = bilerp(tl::lds32(lo + xq[q].x), tl::lds32(lo + xq[q].y), tl::lds32(hi + xq[q].x), tl::lds32(hi + xq[q].y),
                                __uint_as_float(xq[q].z), ly);
-                  ob[((size_t)c * P + py) * P + px] = v;
+                  // streaming store: the block is written once and not read here; keeping it out of L2 leaves the image's
+                  // map resident (67 MB of fp32 P2 + 50 MB of output per image would otherwise thrash the 126 MB L2:
+                  // ncu showed 2.9x the touched map bytes coming from DRAM)
+                  __stcs(ob + ((size_t)c * P + py) * P + px, v);
                 }
               }
             }
@@ -794,7 +838,7 @@ static int roi_levels(mrcnn_ctx* ctx, int batch, const float* d_rois, int roi_st
   if (total > ctx->roi_cap) {
     MRCNN_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->d_roi_level);
-    MRCNN_CUDA_TRY(ctx, cudaMalloc(&ctx->d_roi_level, sizeof(int32_t) * (total + 1)));    // + the ticket counter
+    MRCNN_CUDA_TRY(ctx, cudaMalloc(&ctx->d_roi_level, sizeof(int32_t) * (2 * total + 1)));    // levels, ticket counter, order
     ctx->roi_cap = (int)total;
   }
   // PyramidROIAlignLayer.swift:357 ratio = factor / sqrt(W*H)  (Q15: configured size always used)
@@ -811,7 +855,7 @@ struct RoiTmaEntry {                 // tensor maps of one pyramid (they do not 
   const void* p[4]; int hw[8]; int C, batch; bool chw;
   RoiTmaMaps maps; int box_px[4][8]; int cpx;
 };
-struct RoiTmaCache { std::vector<RoiTmaEntry> entries; int ctas = 2; int rowwise = -1; int slot_px = 0; int mode = -1; int ahead = 0; };
+struct RoiTmaCache { std::vector<RoiTmaEntry> entries; int ctas = 2; int rowwise = -1; int slot_px = 0; int mode = -1; int ahead = 0; int sorted = -1; };
 
 void roialign_release(mrcnn_ctx* ctx) {
   delete (RoiTmaCache*)ctx->roi_tma;
@@ -831,10 +875,28 @@ static RoiTmaCache* roi_cache(mrcnn_ctx* ctx) {
     cache->ctas = en ? std::max(2, std::min(4, atoi(en))) : 2;
     const char* ew = getenv("MRCNN_ROIALIGN_ROWWISE");        // 0 / 1: force the sample-row / feature-row consumer loop
     cache->rowwise = ew ? (atoi(ew) != 0) : -1;
+    const char* eo = getenv("MRCNN_ROIALIGN_SORT");           // 0 / 1: process rois in roi order / sorted by (level, y, x)
+    cache->sorted = eo ? (atoi(eo) != 0) : -1;
     const char* ea = getenv("MRCNN_ROIALIGN_AHEAD");          // 1: the planner asks L2 for a roi's rows when it plans it
     cache->ahead = ea ? std::max(0, std::min(16, atoi(ea))) : 0;
   }
   return cache;
+}
+
+// roi processing order for the staged kernel (nullptr: roi order).  Needs the levels (roi_levels ran on the stream).
+static int roi_order(mrcnn_ctx* ctx, RoiTmaCache* cache, int batch, const float* d_rois, int roi_stride, int64_t R,
+                     bool chw, const int32_t** order) {
+  *order = nullptr;
+  const bool want = cache->sorted >= 0 ? cache->sorted != 0 : chw;    // MRCNN_ROIALIGN_SORT=0/1; default: boundary layout only
+  if (!want || R < 2 || R > 4096) return MRCNN_OK;
+  int n = 2;
+  while (n < R) n <<= 1;
+  int32_t* o = ctx->d_roi_level + ctx->roi_cap + 1;
+  ProfScope ps(ctx, PROF_GLUE, (double)batch * R * (roi_stride * 4 + 8));
+  roi_order_kernel<<<batch, std::min(n, 1024), (size_t)n * 8, ctx->stream>>>(d_rois, roi_stride, (int)R, n, ctx->d_roi_level, o);
+  MRCNN_LAUNCH_CHECK(ctx);
+  *order = o;
+  return MRCNN_OK;
 }
 
 static int roi_tma_entry(mrcnn_ctx* ctx, RoiTmaCache* cache, int batch, const void* const d_fmaps[4],
@@ -865,7 +927,10 @@ static int roi_tma_entry(mrcnn_ctx* ctx, RoiTmaCache* cache, int batch, const vo
       cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)px, 1, 1};
       if (chw) { box[0] = (cuuint32_t)px; box[1] = 1; box[2] = (cuuint32_t)C; }
       CUresult r = enc(&e.maps.m[l][wc], chw ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)d_fmaps[l], dims, str, box, es,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                       // CHW: a box is C separate runs of 16-128 bytes, one per channel plane: promoting each to 256 B
+                       // tripled the DRAM reads (ncu: 1.5 GB read for 0.47 GB touched); NHWC rows are >= 2 KB contiguous
+                       chw ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) {
         char b[160];
@@ -948,7 +1013,7 @@ int roialign_nhwc_f16_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int ro
   RoiTmaCache* cache = roi_cache(ctx);
   // bytes this launch has to move at least: the output once + the rois; the map bytes the rois really touch are
   // data dependent (bench.py reports them from the roi footprints and, under ncu, from dram__bytes)
-  ProfScope ps(ctx, PROF_ROIALIGN, (double)batch * (2.0 * R * C * P * P + 4.0 * R * roi_stride));
+  const double prof_bytes = (double)batch * (2.0 * R * C * P * P + 4.0 * R * roi_stride);
   if (cache->mode == 1 && C <= 256 && P <= 16 && (((uintptr_t)d_fmaps[0] | (uintptr_t)d_fmaps[1] | (uintptr_t)d_fmaps[2] | (uintptr_t)d_fmaps[3]) & 15) == 0) {
     const RoiTmaEntry* e = nullptr;
     rc = roi_tma_entry(ctx, cache, batch, (const void* const*)d_fmaps, hw, (int)C, false, &e);
@@ -956,12 +1021,16 @@ int roialign_nhwc_f16_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int ro
     RoiTmaArgs a;
     a.rois = d_rois; a.roi_stride = roi_stride; a.R = (int)R; a.total = (int)(batch * R);
     a.C = (int)C; a.P = P; a.level = lv; a.out = d_out;
+    rc = roi_order(ctx, cache, batch, d_rois, roi_stride, R, false, &a.order);
+    if (rc) return rc;
     a.pix = (int)C * 2; a.slot_px = cache->slot_px; a.cpx = e->cpx; a.chunk_bytes = e->cpx * (int)C * 2; a.nch = 0; a.ahead = cache->ahead; a.ticket = ctx->d_roi_level + ctx->roi_cap;
     memcpy(a.box_px, e->box_px, sizeof(a.box_px));
     a.negzero = -0.0f; a.pyr = pyr; memset(&a.pyr32, 0, sizeof(a.pyr32));
+    ProfScope ps(ctx, PROF_ROIALIGN, prof_bytes);
     rc = launch_roialign_tma(ctx, cache, e->maps, a);
     if (rc) return rc;
   } else {
+    ProfScope ps(ctx, PROF_ROIALIGN, prof_bytes);
     dim3 grid((unsigned)R, batch);
     roialign_nhwc_kernel<<<grid, 256, 0, ctx->stream>>>(d_rois, roi_stride, (int)R, pyr, (int)C, P, lv, d_out);
   }
@@ -992,7 +1061,7 @@ int roialign_chw_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int roi_str
   const int blk = (int)C * P * P;
   RoiTmaCache* cache = roi_cache(ctx);
   // bytes this launch has to move at least: the output once + the rois (the touched map bytes are data dependent)
-  ProfScope ps(ctx, PROF_ROIALIGN, (double)batch * (4.0 * R * blk + 4.0 * R * roi_stride));
+  const double prof_bytes = (double)batch * (4.0 * R * blk + 4.0 * R * roi_stride);
   if (cache->mode == 1 && tma_ok) {
     const RoiTmaEntry* e = nullptr;
     rc = roi_tma_entry(ctx, cache, batch, (const void* const*)d_fmaps, hw, (int)C, true, &e);
@@ -1000,16 +1069,20 @@ int roialign_chw_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int roi_str
     RoiTmaArgs a;
     a.rois = d_rois; a.roi_stride = roi_stride; a.R = (int)R; a.total = (int)(batch * R);
     a.C = (int)C; a.P = P; a.level = lv; a.out = d_out;
+    rc = roi_order(ctx, cache, batch, d_rois, roi_stride, R, true, &a.order);
+    if (rc) return rc;
     a.pix = 4; a.slot_px = cache->slot_px; a.cpx = e->cpx; a.chunk_bytes = e->cpx * 4 * (int)C; a.nch = 0; a.ahead = 0;
     a.ticket = ctx->d_roi_level + ctx->roi_cap;
     memcpy(a.box_px, e->box_px, sizeof(a.box_px));
     a.negzero = -0.0f; a.pyr32 = pyr;
     for (int l = 0; l < 4; ++l) { a.pyr.p[l] = nullptr; a.pyr.h[l] = pyr.h[l]; a.pyr.w[l] = pyr.w[l]; }
+    ProfScope ps(ctx, PROF_ROIALIGN, prof_bytes);
     if (P == 7) rc = launch_roialign_tma_t<7, 7, 2, false, true>(ctx, e->maps, a);
     else if (P == 14) rc = launch_roialign_tma_t<14, 7, 2, false, true>(ctx, e->maps, a);
     else rc = launch_roialign_tma_t<0, 7, 2, false, true>(ctx, e->maps, a);
     if (rc) return rc;
   } else {
+    ProfScope ps(ctx, PROF_ROIALIGN, prof_bytes);
     dim3 grid(ceil_div(blk, 1024), (unsigned)R, batch);
     roialign_chw_kernel<<<grid, 256, 0, ctx->stream>>>(d_rois, roi_stride, (int)R, pyr, (int)C, P, lv, d_out);
   }
