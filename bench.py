@@ -37,6 +37,15 @@ sys.path.insert(0, ROOT)
 METRIC = "images/sec (1024x1024, 1000 ROIs)"
 UNIT = "images/s"
 IMG = 1024
+# BASELINE.json configs the pipeline workload can be run on: name -> (architecture, image size, proposals, batch or None)
+CONFIGS = {"A": (101, 1024, 1000, None),         # configs[1] (batch 8 per GPU) / configs[3] (8 GPUs): the headline
+           "small": (50, 512, 300, None),        # configs[2]: ResNet50, 512x512, 300 proposals
+           "single": (101, 1024, 1000, 1)}       # configs[0]: one 1024x1024 image per call (latency)
+
+
+def config_metric(name):
+    arch, size, props, _ = CONFIGS[name]
+    return METRIC if name != "small" else f"images/sec ({size}x{size}, {props} ROIs)"
 
 
 # --------------------------------------------------------------------------- utils
@@ -120,14 +129,15 @@ def cpu_custom_layers_image(orc, synth, anchors, image_index, maps):
 _CPU_STATE = {}
 
 
-def cpu_pipeline_image(m, orc, image_index, architecture=101, size=IMG):
+def cpu_pipeline_image(m, orc, image_index, architecture=101, size=IMG, proposals=1000):
     """The reference's whole path for ONE image on the host CPU: dense graphs = oracle/dense_ref.py (PyTorch CPU
     fp32, all host threads; what Core ML's CPU path does with the .mlmodel graphs), custom layers = oracle.c
     (single thread, like the reference's Swift layers).  Returns (seconds, per-stage seconds)."""
     import torch
     from oracle.dense_ref import Ref
     st = _CPU_STATE
-    if "ref" not in st:
+    if st.get("key") != (architecture, size):
+        st["key"] = (architecture, size)
         folded, _ = m.weights.synthetic_blobs(architecture)
         st["ref"] = Ref(folded, architecture, act_half=False, device="cpu")
         st["anchors"] = m.synth.generate_anchors(size, size)
@@ -138,7 +148,7 @@ def cpu_pipeline_image(m, orc, image_index, architecture=101, size=IMG):
     with torch.no_grad():
         fm, probs, deltas = ref.backbone(img)
         t.append(time.perf_counter())
-        rois, _, _ = orc.proposal(probs[0].numpy(), deltas[0].numpy(), anchors)
+        rois, _, _ = orc.proposal(probs[0].numpy(), deltas[0].numpy(), anchors, pre_nms=6000, max_proposals=proposals)
         t.append(time.perf_counter())
         maps = [np.ascontiguousarray(f[0].permute(2, 0, 1).numpy()) for f in fm]      # CHW fp32, the layer's layout
         pooled, _ = orc.pyramid_roialign(rois, maps, 7, size, size)
@@ -153,10 +163,44 @@ def cpu_pipeline_image(m, orc, image_index, architecture=101, size=IMG):
         nv = max(int((lv >= 0).sum()), 1)                # removeZeros: the Mask model only runs on valid blocks
         mk = ref.mask(np.ascontiguousarray(pooled14[:nv].transpose(0, 2, 3, 1))).numpy()
         full = np.zeros((100,) + mk.shape[1:], np.float32); full[:nv] = mk
-        orc.mask_select(full, (lv >= 0).astype(np.int32), det)
+        masks = orc.mask_select(full, (lv >= 0).astype(np.int32), det)
         t.append(time.perf_counter())
     names = ["backbone+fpn+rpn", "proposal", "roialign7", "classifier", "detection", "roialign14", "mask"]
+    st["last_outputs"] = (img, det, masks)          # for the end-to-end agreement check (PipelineWorkload.cpu_baseline)
     return t[-1] - t[0], dict(zip(names, np.diff(t).tolist()))
+
+
+def box_iou(a, b):
+    """IoU of (y1, x1, y2, x2) boxes a [n, 4] against b [m, 4] (float64)."""
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    iy = np.clip(np.minimum(a[:, None, 2], b[None, :, 2]) - np.maximum(a[:, None, 0], b[None, :, 0]), 0, None)
+    ix = np.clip(np.minimum(a[:, None, 3], b[None, :, 3]) - np.maximum(a[:, None, 1], b[None, :, 1]), 0, None)
+    inter = iy * ix
+    aa = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1]); ab = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    return inter / np.maximum(aa[:, None] + ab[None, :] - inter, 1e-30)
+
+
+def detection_agreement(cpu_det, cpu_masks, gpu_det, gpu_masks, iou_thr=0.99):
+    """The reference validates end to end (EvaluateCommand.swift:166-194, COCOEval/task.py:99-105): here, per image, every
+    detection of the fp32 CPU path is matched one-to-one with a GPU detection of the same class and IoU > iou_thr."""
+    nc, ng = int((cpu_det[:, 5] > 0).sum()), int((gpu_det[:, 5] > 0).sum())
+    out = {"cpu": nc, "gpu": ng, "matched": 0, "max_box_delta": 0.0, "max_score_delta": 0.0, "max_mask_delta": 0.0}
+    if nc == 0 or ng == 0:
+        return out
+    iou = box_iou(cpu_det[:nc, :4], gpu_det[:ng, :4])
+    iou[cpu_det[:nc, 4][:, None] != gpu_det[:ng, 4][None, :]] = 0.0
+    used = np.zeros(ng, bool)
+    for i in np.argsort(-cpu_det[:nc, 5], kind="stable"):
+        cand = np.where(~used & (iou[i] > iou_thr))[0]
+        if len(cand) == 0:
+            continue
+        j = cand[np.argmax(iou[i, cand])]
+        used[j] = True
+        out["matched"] += 1
+        out["max_box_delta"] = max(out["max_box_delta"], float(np.abs(cpu_det[i, :4] - gpu_det[j, :4]).max()))
+        out["max_score_delta"] = max(out["max_score_delta"], float(abs(cpu_det[i, 5] - gpu_det[j, 5])))
+        out["max_mask_delta"] = max(out["max_mask_delta"], float(np.abs(cpu_masks[i] - gpu_masks[j]).max()))
+    return out
 
 
 def run_reference(args):
@@ -170,14 +214,15 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     workload = args.workload
     times = []
+    arch, size, props, cfg_batch = CONFIGS[args.config]
     if workload == "pipeline":
         import torch
         torch.set_num_threads(cores)
         for s in range(args.warmup + args.steps):
-            dt, _ = cpu_pipeline_image(m, orc, s)
+            dt, _ = cpu_pipeline_image(m, orc, s, arch, size, props)
             if s >= args.warmup:
                 times.append(dt)
-        sample = ("1 image (1024x1024, ResNet101+FPN, 1000 rois) per step: PyTorch-CPU fp32 dense graphs on all host "
+        sample = (f"1 image ({size}x{size}, ResNet{arch}+FPN, {props} rois) per step: PyTorch-CPU fp32 dense graphs on all host "
                   "threads + oracle.c custom layers (1 thread)")
         kind_cores = cores
     else:
@@ -193,13 +238,13 @@ def run_reference(args):
     ms = 1e3 * float(np.mean(times))
     v = 1e3 / ms
     emit(({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": config_metric(args.config), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         # the same workload as the B200 arm's `config` (one image of that batch per step: a bounded sample)
-        "config": {"workload": workload, "image": "1024x1024x3", "batch_per_gpu": args.batch, "global_batch": args.batch * max(args.gpus, 1),
-                   "pre_nms": 6000, "rois": 1000, "detections": 100,
-                   "model": "ResNet101+FPN Mask-RCNN, 81 classes, synthetic fp16 weights (seed 7)", "sample": sample},
+        "config": {"workload": workload, "image": f"{size}x{size}x3", "batch_per_gpu": args.batch, "global_batch": args.batch * max(args.gpus, 1),
+                   "name": args.config, "pre_nms": 6000, "rois": props, "detections": 100,
+                   "model": f"ResNet{arch}+FPN Mask-RCNN, 81 classes, synthetic fp16 weights (seed 7)", "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": kind_cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -295,11 +340,14 @@ class PipelineWorkload:
     name = "pipeline"
     dtype = "f16"     # tensor-core operands fp16 (as the reference stores its weights), fp32 accumulate; custom layers f32/f64
 
-    def __init__(self, m, torch, device, batch, rank, world, architecture=101, precise_masks=False):
+    def __init__(self, m, torch, device, batch, rank, world, architecture=101, size=IMG, proposals=1000, precise_masks=True):
         self.m, self.torch, self.b, self.world = m, torch, batch, world
+        self.arch, self.size, self.props = architecture, size, proposals
+        IMG = size                                                # (shadows the module constant: everything below is per config)
         cfg = m.MaskRCNNConfig()
         cfg.preciseMasks = bool(precise_masks)
         cfg.architecture = "resnet101" if architecture == 101 else "resnet50"
+        cfg.imageShape, cfg.maxProposals = (size, size, 3), proposals
         cfg.maxBatch = batch
         _, blobs = m.weights.synthetic_blobs(architecture)
         self.model = m.MaskRCNN(cfg, device=device, blobs=blobs, anchors=m.synth.generate_anchors(IMG, IMG))
@@ -321,10 +369,10 @@ class PipelineWorkload:
         self.h_mask2 = [self.h_mask, torch.zeros((tot, 100, 28, 28)).pin_memory()]
         self.h2d = self.h_img.numel()
         self.d2h = 4 * (self.h_det.numel() + self.h_mask.numel())
-        self.config_extra = {"model": "ResNet101+FPN Mask-RCNN, 81 classes, synthetic fp16 weights (seed 7)",
+        self.config_extra = {"model": f"ResNet{architecture}+FPN Mask-RCNN, 81 classes, synthetic fp16 weights (seed 7)",
                              "collective": "none" if world == 1 else "1 ncclAllGather of packed detections|masks per step",
-                             "mask_head": "2-term fp16 activations (masks within 1e-4 of fp32)" if precise_masks else
-                                          "fp16 activations (masks within 5e-4 of fp32)"}
+                             "mask_head": "2-term fp16 activations: masks <= 1e-4 from an fp32 evaluation of the head (library default)" if precise_masks else
+                                          "1-term fp16 activations (precise_masks = 0): masks within 5e-4 of fp32"}
         if world > 1:
             import torch.distributed as dist
             uid = torch.zeros(128, dtype=torch.uint8)
@@ -346,6 +394,25 @@ class PipelineWorkload:
 
     def step(self):
         self._predict(self.d_img, self.d_det, self.d_mask)
+
+    def verify_gather(self, dist, rank):
+        """Outside the timed region, on hardware: slice r of the all-gathered detections / masks equals rank r's own
+        mrcnn_predict of its images, bit for bit, and every rank holds identical gathered buffers (checksums all-reduced)."""
+        torch = self.torch
+        l, h, b = self.m.lib(), self.ctx.handle, self.b
+        with torch.cuda.stream(self.stream):
+            self._predict(self.d_img, self.d_det, self.d_mask)                       # gathered: [world * b, ...]
+            ldet = torch.zeros((b, 100, 6), device="cuda"); lmask = torch.zeros((b, 100, 28, 28), device="cuda")
+            self.m._cabi.check(h, l.mrcnn_predict(h, b, self.d_img.data_ptr(), ldet.data_ptr(), lmask.data_ptr()))
+        self.stream.synchronize()
+        mine = bool(torch.equal(self.d_det[rank * b:(rank + 1) * b], ldet) and torch.equal(self.d_mask[rank * b:(rank + 1) * b], lmask))
+        nonzero = bool((ldet[..., 5] > 0).any())
+        cs = (self.d_det.view(torch.int32).to(torch.int64).sum() * 31 + self.d_mask.view(torch.int32).to(torch.int64).sum()).reshape(1)
+        lo, hi = cs.clone(), cs.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ok = torch.tensor([int(mine and nonzero and int(lo.item()) == int(hi.item()))], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        return bool(ok.item())
 
     def step_e2e(self):
         # the reference-facing call with HOST buffers: H2D of the images and D2H of detections + masks happen inside
@@ -396,152 +463,31 @@ class PipelineWorkload:
         orc.lib()
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        cpu_pipeline_image(self.m, orc, 1000)                       # warm-up (weights to torch, page-in)
-        runs = [cpu_pipeline_image(self.m, orc, i) for i in range(4)]
+        arch, size = self.arch, self.size
+        cpu_pipeline_image(self.m, orc, 1000, arch, size, self.props)           # warm-up (weights to torch, page-in)
+        runs, agree = [], []
+        for i in range(4):
+            runs.append(cpu_pipeline_image(self.m, orc, i, arch, size, self.props))
+            # the SAME image through the GPU path: how far is the fp16-activation tensor-core pipeline from the fp32 CPU one?
+            img, cdet, cmask = _CPU_STATE["last_outputs"]
+            gdet, gmask = self.model.prediction_batch(img)
+            agree.append(detection_agreement(cdet, cmask, gdet[0], gmask[0]))
         dt = float(np.mean([r[0] for r in runs]))
         stages = {k: float(np.mean([r[1][k] for r in runs])) for k in runs[0][1]}
+        tot = {k: (sum(a[k] for a in agree) if k in ("cpu", "gpu", "matched") else max(a[k] for a in agree)) for k in agree[0]}
+        self.e2e_agreement = dict(tot, images=len(agree), rule="same class and IoU > 0.99, one to one; deltas over the matched detections",
+                                  note="GPU: fp16 activations in backbone / classifier head (2-term in the mask head); CPU: fp32 everywhere, same fp16-stored weights")
         return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": "4 images of the same workload after 1 warm-up image: PyTorch-CPU fp32 dense graphs (all host threads) "
                           "+ oracle.c custom layers (1 thread)", "stage_seconds": stages}
 
 
-# --------------------------------------------------------------------------- ROIAlign microbench (configs[4])
-ROI_METRIC = "ROIAlign HBM GB/s (1000 ROIs x P2 256x256x256 tiles)"
-ROI_HEADLINE = ("nhwc_f16", 8, 1000, 7)
-
-
-def roialign_cpu(orc, batch_images=1, r=1000, pool=7, reps=3):
-    """The reference's ROIAlign on the host CPU: oracle.c crop_and_resize (scalar, one thread, CHW fp32 = the layer's own
-    layout) on the same level-2 rois; returns (seconds per image, bytes per image by the touched model)."""
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
-    import bench_roialign as br
-    rng = np.random.default_rng(5)
-    maps = [rng.standard_normal((256, s, s), dtype=np.float32) for s in (256, 128, 64, 32)]
-    ts, byts = [], 0
-    for i in range(batch_images * reps):
-        rois = br.level2_rois(r, 100 * i + r)
-        t0 = time.perf_counter()
-        orc.pyramid_roialign(rois, maps, pool)
-        ts.append(time.perf_counter() - t0)
-        byts = br.touched_map_bytes(rois, 256, 256, 256, pool, "chw_f32") + r * 256 * pool * pool * 4 + r * 16
-    return float(np.median(ts)), byts
-
-
-def run_roialign(args):
-    """BASELINE.json configs[4].  One "step" = one ROIAlign launch over the batch (level kernel + ROIAlign kernel).  value
-    = GB/s of the headline case (internal NHWC fp16 layout, batch 8, 1000 rois, pool 7) on the TOUCHED-bytes model
-    (tools/bench_roialign.py); the SURVEY 8(d) whole-map model and the ncu DRAM bytes are reported beside it."""
-    rank, world, local = dist_env()
-    if rank != 0:
-        return                                                # independent replicas would measure the same thing
-    import torch
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
-    torch.cuda.set_device(local)
-    import maskrcnn_b200 as m
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
-    import bench_roialign as br
-    peaks = load_peaks()
-    sampler = ClockSampler(local)
-    sampler.start()
-    cases = None
-    if args.quick:
-        cases = [ROI_HEADLINE, ("nhwc_f16", 8, 1000, 14), ("nhwc_f16", 1, 1000, 7), ("chw_f32", 1, 1000, 7), ("chw_f32", 8, 1000, 7)]
-    rows = br.sweep(m, torch, cases, iters=max(args.steps, 4), log=lambda s: sys.stderr.write(s + "\n"))
-    clocks = sampler.stop()
-    head = next(r for r in rows if (r["layout"], r["batch"], r["rois"], r["pool"]) == ROI_HEADLINE)
-    chw = next((r for r in rows if (r["layout"], r["batch"], r["rois"], r["pool"]) == ("chw_f32", 8, 1000, 7)), None)
-    # end to end: the layer call with HOST buffers (maps, rois in; pooled features out), copies inside the timed region
-    ctx = m.Context()
-    st = torch.cuda.Stream(); ctx.set_stream(st.cuda_stream)
-    b, r, pool = 8, 1000, 7
-    hmaps = [torch.randn((b, 256, s, s)).pin_memory() for s in (256, 128, 64, 32)]
-    hrois = torch.from_numpy(np.stack([br.level2_rois(r, 100 * i + r) for i in range(b)])).pin_memory()
-    hout = torch.empty((b, r, 256, pool, pool)).pin_memory()
-    layer = m.PyramidROIAlignLayer({"poolSize": pool}, context=ctx)
-    ts = []
-    for it in range(4):
-        t0 = time.perf_counter()
-        layer.evaluate([hrois] + hmaps, [hout])
-        ts.append(time.perf_counter() - t0)
-    e2e_s = float(np.median(ts[1:]))
-    h2d = sum(x.numel() * 4 for x in hmaps) + hrois.numel() * 4
-    d2h = hout.numel() * 4
-    e2e_bytes = sum(br.touched_map_bytes(hrois[i].numpy(), 256, 256, 256, pool, "chw_f32") for i in range(b)) + d2h + hrois.numel() * 4
-    ctx.close()
-    line = {
-        "metric": ROI_METRIC, "value": head["GBps_touched"], "unit": "GB/s", "n_gpus": 1, "steps": max(args.steps, 4),
-        "warmup": 2, "ms_per_step": head["us_call"] * 1e-3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16 maps / f32 arithmetic (internal NHWC layout); f32 (boundary CHW layout)", "data": "synthetic",
-        "config": {"workload": "roialign", "case": head["case"], "fmap": "P2 256x256x256 per image", "rois_per_image": 1000,
-                   "batch": 8, "pool": 7, "rois": "level 2 only: sqrt(w*h) in [12, 75] px, log-uniform, seeded",
-                   "l2_policy": "256 MB memset before every timed launch"},
-        "clocks": clocks,
-        "e2e": {"value": e2e_bytes / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "mode": "mrcnn_pyramid_roialign_eval (boundary CHW fp32 layout) with pinned HOST maps / rois / output, one blocking "
-                        "call per step; the 716 MB of feature maps cross PCIe every call, as they cross to the GPU in the reference "
-                        "(PyramidROIAlignLayer.swift:110-118)", "seconds_per_step": e2e_s},
-        "gpu_launches": 2 * (max(args.steps, 4) + 2),
-        "roofline": {"kernel": "roialign_staged_kernel<7, 7, 2, false, false> (NHWC fp16)", "bound": "hbm", "achieved": head["GBps_touched"],
-                     "peak": peaks["hbm"], "peak_source": peaks["source"], "unit": "GB/s", "frac": head["frac"],
-                     "algorithmic_bytes_per_launch": head["bytes_touched"], "avg_launch_us": head["us_kernel"],
-                     "achieved_survey_model": head["GBps_survey"], "frac_survey_model": head["frac_survey"],
-                     "achieved_dram": head["GBps_dram_ncu"], "frac_dram": head["frac_dram_ncu"], "traffic": head["bytes_dram_ncu"],
-                     "note": "achieved = (map bytes the rois touch, 32-B sectors + output + rois) / kernel time; survey model charges "
-                             "the whole P2 map (SURVEY.md 8(d)); achieved_dram = ncu dram__bytes of the same launch / kernel time"},
-        "roofline_chw_f32": None if chw is None else {"kernel": "roialign_staged_kernel<7, 7, 2, false, true> (boundary CHW fp32)", "bound": "hbm", "achieved": chw["GBps_touched"],
-                                                      "peak": peaks["hbm"], "unit": "GB/s", "frac": chw["frac"], "frac_survey_model": chw["frac_survey"],
-                                                      "achieved_dram": chw["GBps_dram_ncu"], "frac_dram": chw["frac_dram_ncu"], "avg_launch_us": chw["us_kernel"]},
-        "sweep": rows,
-    }
-    if not args.no_cpu_baseline:
-        from oracle import oracle as orc
-        orc.lib()
-        sec, byts = roialign_cpu(orc)
-        line["cpu_baseline"] = {"value": byts / sec / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
-                                "sample": "1 image (1000 level-2 rois, pool 7, CHW fp32) x 3, oracle.c crop_and_resize, single thread "
-                                          "like the reference's layer code", "seconds_per_image": sec}
-    emit(line)
-
-
-def run_roialign_reference(args):
-    """The reference's ROIAlign on the host: oracle.c crop_and_resize, one image per host thread (the layer itself is
-    single-threaded; images are independent, so all cores are used by running `cores` images side by side)."""
-    rank, _, _ = dist_env()
-    if rank != 0:
-        return
-    from concurrent.futures import ThreadPoolExecutor
-    from oracle import oracle as orc
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
-    import bench_roialign as br
-    orc.lib()
-    cores = os.cpu_count() or 1
-    rng = np.random.default_rng(5)
-    maps = [rng.standard_normal((256, s, s), dtype=np.float32) for s in (256, 128, 64, 32)]
-    rois = [br.level2_rois(1000, 100 * i + 1000) for i in range(cores)]
-    byts = sum(br.touched_map_bytes(r, 256, 256, 256, 7, "chw_f32") + 1000 * 256 * 49 * 4 + 16000 for r in rois)
-    ts = []
-    with ThreadPoolExecutor(cores) as ex:
-        for s in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            list(ex.map(lambda r: orc.pyramid_roialign(r, maps, 7), rois))       # ctypes releases the GIL
-            if s >= args.warmup:
-                ts.append(time.perf_counter() - t0)
-    sec = float(np.mean(ts))
-    v = byts / sec / 1e9
-    sample = (f"{cores} images per step, one per host thread (1000 level-2 rois each, pool 7, CHW fp32): oracle.c crop_and_resize")
-    emit({"impl": "reference", "metric": ROI_METRIC, "value": v, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
-          "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-          "dtype": "f32", "data": "synthetic",
-          "config": {"workload": "roialign", "case": "chw_f32,1,1000,7", "fmap": "P2 256x256x256 per image", "rois_per_image": 1000,
-                     "batch": 8, "pool": 7, "sample": sample},
-          "cpu_baseline": {"value": v, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
-          "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-
-
 def make_workload(args, m, torch, device):
     rank, world, _ = dist_env()
     if args.workload == "pipeline":
-        return PipelineWorkload(m, torch, device, args.batch, rank, world, precise_masks=args.precise_masks)
+        arch, size, props, _ = CONFIGS[args.config]
+        return PipelineWorkload(m, torch, device, args.batch, rank, world, architecture=arch, size=size, proposals=props,
+                                precise_masks=args.precise_masks)
     return CustomLayersWorkload(m, torch, device, args.batch, 0)
 
 
@@ -613,7 +559,10 @@ def run_ours(args):
         e2e_mode = ("streaming: mrcnn_predict_submit / mrcnn_predict_wait, two batches in flight, pinned host buffers; "
                     "every step's H2D and D2H inside the timed region, which ends after the last batch's results are in host memory")
 
+    gather_verified = None
     if world > 1:
+        if hasattr(wl, "verify_gather"):
+            gather_verified = wl.verify_gather(dist, rank)
         dist.barrier()
     if rank != 0:
         if world > 1:
@@ -623,11 +572,12 @@ def run_ours(args):
     ms_step = total_ms / args.steps
     imgs = args.batch * world
     line = {
-        "metric": METRIC, "value": imgs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": config_metric(args.config), "value": imgs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-        "config": dict({"workload": wl.name, "image": "1024x1024x3", "batch_per_gpu": args.batch, "global_batch": imgs,
-                        "pre_nms": 6000, "rois": 1000, "detections": 100,
+        "config": dict({"workload": wl.name, "name": args.config, "image": f"{CONFIGS[args.config][1]}x{CONFIGS[args.config][1]}x3",
+                        "batch_per_gpu": args.batch, "global_batch": imgs,
+                        "pre_nms": 6000, "rois": CONFIGS[args.config][2], "detections": 100,
                         "l2_policy": "per-step working set (batch activations + feature maps, > 1 GB) exceeds the 126 MB L2; no explicit flush"},
                        **getattr(wl, "config_extra", {})),
         "clocks": clocks,
@@ -636,6 +586,7 @@ def run_ours(args):
                 "sync_value": imgs / (e2e_sync_ms / args.steps * 1e-3),
                 "sync_mode": "mrcnn_predict with host buffers, one blocking call per step (copies serialised with compute)"},
         "gpu_launches": launches * args.steps,
+        "gather_verified": gather_verified,       # N > 1: gathered slice r == rank r's local predict, identical buffers on all ranks
         "roofline": wl.roofline(prof, peaks),
         "kernel_classes": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps,
                                "work_per_step": v[2] / args.steps} for k, v in prof.items() if v[1]},
@@ -644,6 +595,8 @@ def run_ours(args):
         line.update(wl.extra_rooflines(prof, peaks))
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = wl.cpu_baseline() if hasattr(wl, "cpu_baseline") else default_cpu_baseline(m)
+        if hasattr(wl, "e2e_agreement"):
+            line["e2e_agreement"] = wl.e2e_agreement
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -685,12 +638,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, "pipeline", "custom_layers", "roialign"])
     ap.add_argument("--quick", action="store_true", help="roialign: the headline cases only instead of the whole sweep")
-    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step (configs[1]: 8)")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default 8 = configs[1]; 1 for --config single)")
+    ap.add_argument("--config", default="A", choices=sorted(CONFIGS), help="A: ResNet101 1024x1024 1000 rois (headline); small: ResNet50 "
+                    "512x512 300 rois (configs[2]); single: A with one image per call (configs[0], latency)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precise-masks", type=int, default=0, help="1: 2-term fp16 activations in the mask head (mrcnn_config.precise_masks)")
+    ap.add_argument("--precise-masks", type=int, default=1, help="1 (default): 2-term fp16 activations in the mask head, masks within 1e-4 of fp32; 0: 1-term, 5e-4")
     args = ap.parse_args()
     if args.workload is None:
         args.workload = "pipeline"
+    if args.batch is None:
+        args.batch = CONFIGS[args.config][3] or 8
     if args.workload == "roialign":
         (run_roialign_reference if args.impl == "reference" else run_roialign)(args)
     elif args.impl == "reference":

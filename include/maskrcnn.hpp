@@ -123,7 +123,7 @@ class MaskRCNNConfig {
   float scoreThreshold = 0.7f;                            // DetectionLayer.swift:59
   float detectionNMSIOUThreshold = 0.3f;                  // DetectionLayer.swift:61
   int maxBatch = 8;                                       // images per predict call the workspace is sized for
-  bool preciseMasks = false;                              // mrcnn_config.precise_masks
+  bool preciseMasks = true;                               // mrcnn_config.precise_masks (default: masks within 1e-4 of fp32)
   int device = -1;                                        // CUDA ordinal, -1 = current
 
   // The C struct; the returned pointers into *this stay valid while *this is unchanged.

@@ -36,7 +36,7 @@ void mrcnn_config_default(mrcnn_config* c) {
   c->detection_nms_iou = 0.3f;                     // DetectionLayer.swift:61
   c->mean_rgb[0] = 123.7f; c->mean_rgb[1] = 116.8f; c->mean_rgb[2] = 103.9f;  // Conversion/task.py:73-75
   c->max_batch = 8;
-  c->precise_masks = 0;
+  c->precise_masks = 1;      // masks within 1e-4 of an fp32 evaluation (the tolerance of the path); 0 = faster, 5e-4
 }
 
 const char* mrcnn_version(void) { return "maskrcnn_cuda 0.2 (sm_100a, abi 2)"; }

@@ -29,7 +29,7 @@ class MaskRCNNConfig:
         self.maxProposals = 1000                  # ProposalLayer.swift:61
         self.maxDetections = 100                  # DetectionLayer.swift:57
         self.maxBatch = 8
-        self.preciseMasks = False                 # 2-term fp16 activations in the mask head (masks within 1e-4 of fp32)
+        self.preciseMasks = True                  # 2-term fp16 activations in the mask head (masks within 1e-4 of fp32); False: 1-term, 5e-4, ~8 % faster
 
     def context_overrides(self):
         return dict(image_h=self.imageShape[0], image_w=self.imageShape[1],

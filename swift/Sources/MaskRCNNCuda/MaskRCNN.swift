@@ -28,7 +28,7 @@ public class MaskRCNNConfig {
     public var maxProposals: Int32 = 1000
     public var maxDetections: Int32 = 100
     public var maxBatch: Int32 = 8
-    public var preciseMasks = false                 // mrcnn_config.precise_masks: 2-term fp16 activations in the mask head
+    public var preciseMasks = true                  // mrcnn_config.precise_masks: 2-term fp16 activations in the mask head (masks within 1e-4 of fp32)
 }
 
 public struct Detection {

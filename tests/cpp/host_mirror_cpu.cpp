@@ -86,7 +86,7 @@ int main(int argc, char** argv) {
     CHECK(c.num_classes == ref.num_classes && c.pre_nms_max_proposals == ref.pre_nms_max_proposals && c.max_proposals == ref.max_proposals);
     CHECK(c.proposal_nms_iou == ref.proposal_nms_iou && c.detection_min_score == ref.detection_min_score && c.detection_nms_iou == ref.detection_nms_iou);
     CHECK(c.pool_size_classifier == ref.pool_size_classifier && c.pool_size_mask == ref.pool_size_mask && c.max_detections == ref.max_detections);
-    CHECK(c.fpn_selection_factor == ref.fpn_selection_factor && c.max_batch == ref.max_batch && c.precise_masks == 0);
+    CHECK(c.fpn_selection_factor == ref.fpn_selection_factor && c.max_batch == ref.max_batch && c.precise_masks == 1);
     for (int i = 0; i < 4; ++i) CHECK(c.bbox_std[i] == ref.bbox_std[i]);
     for (int i = 0; i < 3; ++i) CHECK(c.mean_rgb[i] == ref.mean_rgb[i]);
     CHECK(!c.anchors_path && !c.main_model_path && !c.classifier_model_path && !c.mask_model_path);

@@ -9,6 +9,10 @@ pytestmark = pytest.mark.gpu
 def _conv_ref(x, w, bias, stride, pad, residual, relu):
     import torch
     import torch.nn.functional as F
+    # a real fp32 reference: cuDNN / cuBLAS may otherwise run fp32 convolutions in TF32 (10-bit mantissa, the precision
+    # of the kernel under test) on this GPU
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     y = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, stride=stride, padding=pad)
     y = y.permute(0, 2, 3, 1)
     if residual is not None:

@@ -87,8 +87,12 @@ def test_classifier_head_vs_torch(pkg, small):
 
 
 def test_mask_head_vs_torch(pkg, small):
+    """The library default (precise_masks = 1, 2-term fp16 activations): the mask head matches a PURE fp32 evaluation of
+    the same head within the 1e-4 of the path (BASELINE.json north_star; TimeDistributedMaskLayer.swift:58-89 returns
+    fp32-from-Double planes)."""
     from oracle.dense_ref import Ref
     m = small["model"]
+    assert m.ctx.cfg.precise_masks == 1
     rng = np.random.default_rng(6)
     d = 100
     pooled = rng.standard_normal((1, d, 256, 14, 14)).astype(np.float16).astype(np.float32)
@@ -98,9 +102,9 @@ def test_mask_head_vs_torch(pkg, small):
     det[0, :60, 5] = 0.9
     out = np.full((1, d, 28, 28), 7.0, np.float32)
     pkg.TimeDistributedMaskLayer(context=m.ctx).evaluate([pooled, det], [out])
-    ref = Ref(small["folded"], 50).mask(pooled[0, :60].transpose(0, 2, 3, 1)).cpu().numpy()
+    ref = Ref(small["folded"], 50, act_half=False).mask(pooled[0, :60].transpose(0, 2, 3, 1)).cpu().numpy()
     want = ref[np.arange(60), det[0, :60, 4].astype(int)]
-    np.testing.assert_allclose(out[0, :60], want, atol=2e-3)                               # measured 4.9e-4
+    np.testing.assert_allclose(out[0, :60], want, rtol=0, atol=1e-4)                       # the tolerance of the path
     assert not out[0, 60:].any()                                  # TimeDistributedMaskLayer.swift:87-89
     assert 0.05 < out[0, :60].std()
 
@@ -167,13 +171,14 @@ def test_missing_weights_fail_loudly(pkg):
     c.close()
 
 
-def test_mask_head_precise_mode_within_1e4_of_fp32(pkg, small):
-    """precise_masks = 1: 2-term (hi, lo) fp16 activations through the tensor cores; the mask head then matches a PURE
-    fp32 evaluation within the north star's 1e-4 (the default fp16-activation mode is within 5e-4)."""
+def test_mask_head_one_term_mode(pkg, small):
+    """precise_masks = 0 (opt-in, ~8 % more images/s): 1-term fp16 activations; the head is then within 1e-3 of fp32
+    (measured 4.9e-4) -- outside the 1e-4 of the path, which is why it is not the default.  Detections do not depend on
+    the mask mode; the whole pipeline keeps its invariants."""
     from oracle.dense_ref import Ref
     cfg = pkg.MaskRCNNConfig()
     cfg.architecture, cfg.imageShape, cfg.preNMSMaxProposals, cfg.maxProposals, cfg.maxBatch = "resnet50", (SIZE, SIZE, 3), 1000, 200, 2
-    cfg.preciseMasks = True
+    cfg.preciseMasks = False
     _, blobs = pkg.weights.synthetic_blobs(50)
     model = pkg.MaskRCNN(cfg, blobs=blobs, anchors=small["anchors"])
     rng = np.random.default_rng(6)
@@ -188,9 +193,8 @@ def test_mask_head_precise_mode_within_1e4_of_fp32(pkg, small):
     ref = Ref(small["folded"], 50, act_half=False).mask(pooled[0, :70].transpose(0, 2, 3, 1)).cpu().numpy()
     want = ref[np.arange(70), det[0, :70, 4].astype(int)]
     err = np.abs(out[0, :70] - want).max()
-    assert err < 1e-4, err
+    assert 1e-5 < err < 1e-3, err
     assert not out[0, 70:].any()
-    # the whole pipeline runs in this mode too and keeps its invariants
     dets, masks = model.prediction_batch(small["img"])
     n = int((dets[0, :, 5] > 0).sum())
     assert n > 0 and ((masks[0, :n] > 0) & (masks[0, :n] < 1)).all() and (masks[0, n:] == 0).all()
