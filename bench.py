@@ -482,6 +482,139 @@ class PipelineWorkload:
                           "+ oracle.c custom layers (1 thread)", "stage_seconds": stages}
 
 
+# --------------------------------------------------------------------------- ROIAlign microbench (configs[4])
+ROI_METRIC = "ROIAlign HBM GB/s (1000 ROIs x P2 256x256x256 tiles)"
+ROI_HEADLINE = ("nhwc_f16", 8, 1000, 7)
+
+
+def roialign_cpu(orc, batch_images=1, r=1000, pool=7, reps=3):
+    """The reference's ROIAlign on the host CPU: oracle.c crop_and_resize (scalar, one thread, CHW fp32 = the layer's own
+    layout) on the same level-2 rois; returns (seconds per image, bytes per image by the touched model)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_roialign as br
+    rng = np.random.default_rng(5)
+    maps = [rng.standard_normal((256, s, s), dtype=np.float32) for s in (256, 128, 64, 32)]
+    ts, byts = [], 0
+    for i in range(batch_images * reps):
+        rois = br.level2_rois(r, 100 * i + r)
+        t0 = time.perf_counter()
+        orc.pyramid_roialign(rois, maps, pool)
+        ts.append(time.perf_counter() - t0)
+        byts = br.touched_map_bytes(rois, 256, 256, 256, pool, "chw_f32") + r * 256 * pool * pool * 4 + r * 16
+    return float(np.median(ts)), byts
+
+
+def run_roialign(args):
+    """BASELINE.json configs[4].  One "step" = one ROIAlign launch over the batch (level kernel + ROIAlign kernel).  value
+    = GB/s of the headline case (internal NHWC fp16 layout, batch 8, 1000 rois, pool 7) on the TOUCHED-bytes model
+    (tools/bench_roialign.py); the SURVEY 8(d) whole-map model and the ncu DRAM bytes are reported beside it."""
+    rank, world, local = dist_env()
+    if rank != 0:
+        return                                                # independent replicas would measure the same thing
+    import torch
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    import maskrcnn_b200 as m
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_roialign as br
+    peaks = load_peaks()
+    sampler = ClockSampler(local)
+    sampler.start()
+    cases = None
+    if args.quick:
+        cases = [ROI_HEADLINE, ("nhwc_f16", 8, 1000, 14), ("nhwc_f16", 1, 1000, 7), ("chw_f32", 1, 1000, 7), ("chw_f32", 8, 1000, 7)]
+    rows = br.sweep(m, torch, cases, iters=max(args.steps, 4), log=lambda s: sys.stderr.write(s + "\n"))
+    clocks = sampler.stop()
+    head = next(r for r in rows if (r["layout"], r["batch"], r["rois"], r["pool"]) == ROI_HEADLINE)
+    chw = next((r for r in rows if (r["layout"], r["batch"], r["rois"], r["pool"]) == ("chw_f32", 8, 1000, 7)), None)
+    # end to end: the layer call with HOST buffers (maps, rois in; pooled features out), copies inside the timed region
+    ctx = m.Context()
+    st = torch.cuda.Stream(); ctx.set_stream(st.cuda_stream)
+    b, r, pool = 8, 1000, 7
+    hmaps = [torch.randn((b, 256, s, s)).pin_memory() for s in (256, 128, 64, 32)]
+    hrois = torch.from_numpy(np.stack([br.level2_rois(r, 100 * i + r) for i in range(b)])).pin_memory()
+    hout = torch.empty((b, r, 256, pool, pool)).pin_memory()
+    layer = m.PyramidROIAlignLayer({"poolSize": pool}, context=ctx)
+    ts = []
+    for it in range(4):
+        t0 = time.perf_counter()
+        layer.evaluate([hrois] + hmaps, [hout])
+        ts.append(time.perf_counter() - t0)
+    e2e_s = float(np.median(ts[1:]))
+    h2d = sum(x.numel() * 4 for x in hmaps) + hrois.numel() * 4
+    d2h = hout.numel() * 4
+    e2e_bytes = sum(br.touched_map_bytes(hrois[i].numpy(), 256, 256, 256, pool, "chw_f32") for i in range(b)) + d2h + hrois.numel() * 4
+    ctx.close()
+    line = {
+        "metric": ROI_METRIC, "value": head["GBps_touched"], "unit": "GB/s", "n_gpus": 1, "steps": max(args.steps, 4),
+        "warmup": 2, "ms_per_step": head["us_call"] * 1e-3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 maps / f32 arithmetic (internal NHWC layout); f32 (boundary CHW layout)", "data": "synthetic",
+        "config": {"workload": "roialign", "case": head["case"], "fmap": "P2 256x256x256 per image", "rois_per_image": 1000,
+                   "batch": 8, "pool": 7, "rois": "level 2 only: sqrt(w*h) in [12, 75] px, log-uniform, seeded",
+                   "l2_policy": "256 MB memset before every timed launch"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_bytes / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "mode": "mrcnn_pyramid_roialign_eval (boundary CHW fp32 layout) with pinned HOST maps / rois / output, one blocking "
+                        "call per step; the 716 MB of feature maps cross PCIe every call, as they cross to the GPU in the reference "
+                        "(PyramidROIAlignLayer.swift:110-118)", "seconds_per_step": e2e_s},
+        "gpu_launches": 2 * (max(args.steps, 4) + 2),
+        "roofline": {"kernel": "roialign_staged_kernel<7, 7, 2, false, false> (NHWC fp16)", "bound": "hbm", "achieved": head["GBps_touched"],
+                     "peak": peaks["hbm"], "peak_source": peaks["source"], "unit": "GB/s", "frac": head["frac"],
+                     "algorithmic_bytes_per_launch": head["bytes_touched"], "avg_launch_us": head["us_kernel"],
+                     "achieved_survey_model": head["GBps_survey"], "frac_survey_model": head["frac_survey"],
+                     "achieved_dram": head["GBps_dram_ncu"], "frac_dram": head["frac_dram_ncu"], "traffic": head["bytes_dram_ncu"],
+                     "note": "achieved = (map bytes the rois touch, 32-B sectors + output + rois) / kernel time; survey model charges "
+                             "the whole P2 map (SURVEY.md 8(d)); achieved_dram = ncu dram__bytes of the same launch / kernel time"},
+        "roofline_chw_f32": None if chw is None else {"kernel": "roialign_staged_kernel<7, 7, 2, false, true> (boundary CHW fp32)", "bound": "hbm", "achieved": chw["GBps_touched"],
+                                                      "peak": peaks["hbm"], "unit": "GB/s", "frac": chw["frac"], "frac_survey_model": chw["frac_survey"],
+                                                      "achieved_dram": chw["GBps_dram_ncu"], "frac_dram": chw["frac_dram_ncu"], "avg_launch_us": chw["us_kernel"]},
+        "sweep": rows,
+    }
+    if not args.no_cpu_baseline:
+        from oracle import oracle as orc
+        orc.lib()
+        sec, byts = roialign_cpu(orc)
+        line["cpu_baseline"] = {"value": byts / sec / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+                                "sample": "1 image (1000 level-2 rois, pool 7, CHW fp32) x 3, oracle.c crop_and_resize, single thread "
+                                          "like the reference's layer code", "seconds_per_image": sec}
+    emit(line)
+
+
+def run_roialign_reference(args):
+    """The reference's ROIAlign on the host: oracle.c crop_and_resize, one image per host thread (the layer itself is
+    single-threaded; images are independent, so all cores are used by running `cores` images side by side)."""
+    rank, _, _ = dist_env()
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as orc
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_roialign as br
+    orc.lib()
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(5)
+    maps = [rng.standard_normal((256, s, s), dtype=np.float32) for s in (256, 128, 64, 32)]
+    rois = [br.level2_rois(1000, 100 * i + 1000) for i in range(cores)]
+    byts = sum(br.touched_map_bytes(r, 256, 256, 256, 7, "chw_f32") + 1000 * 256 * 49 * 4 + 16000 for r in rois)
+    ts = []
+    with ThreadPoolExecutor(cores) as ex:
+        for s in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            list(ex.map(lambda r: orc.pyramid_roialign(r, maps, 7), rois))       # ctypes releases the GIL
+            if s >= args.warmup:
+                ts.append(time.perf_counter() - t0)
+    sec = float(np.mean(ts))
+    v = byts / sec / 1e9
+    sample = (f"{cores} images per step, one per host thread (1000 level-2 rois each, pool 7, CHW fp32): oracle.c crop_and_resize")
+    emit({"impl": "reference", "metric": ROI_METRIC, "value": v, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+          "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": "f32", "data": "synthetic",
+          "config": {"workload": "roialign", "case": "chw_f32,1,1000,7", "fmap": "P2 256x256x256 per image", "rois_per_image": 1000,
+                     "batch": 8, "pool": 7, "sample": sample},
+          "cpu_baseline": {"value": v, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
+          "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
 def make_workload(args, m, torch, device):
     rank, world, _ = dist_env()
     if args.workload == "pipeline":

@@ -11,7 +11,7 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def test_committed_gpu_line_has_the_contract_keys():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r1w_pipeline_bench_final.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2b_pipeline_bench_A.json")))
     assert BASE_KEYS | {"clocks", "gpu_launches", "roofline"} <= set(d)
     assert d["metric"].startswith("images/sec") and d["unit"] == "images/s" and d["higher_is_better"] is True
     assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
@@ -25,6 +25,9 @@ def test_committed_gpu_line_has_the_contract_keys():
     c = d["cpu_baseline"]
     assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
     assert d["gpu_launches"] > 0 and {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    a = d["e2e_agreement"]                                                  # same images through the CPU port and the GPU path
+    assert a["images"] >= 4 and a["cpu"] > 0 and a["matched"] >= 0.95 * a["cpu"] and a["max_box_delta"] < 1e-3
+    assert "1e-4" in d["config"]["mask_head"]
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
 
 
@@ -35,10 +38,26 @@ def test_reference_arm_prints_the_same_metric_and_config():
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1                                                  # ONE JSON line on stdout
     d = json.loads(lines[0])
-    gpu = json.load(open(os.path.join(ROOT, "profiles", "r1w_pipeline_bench_final.json")))
+    gpu = json.load(open(os.path.join(ROOT, "profiles", "r2b_pipeline_bench_A.json")))
     assert d["impl"] == "reference" and BASE_KEYS <= set(d)
     assert (d["metric"], d["unit"], d["higher_is_better"]) == (gpu["metric"], gpu["unit"], gpu["higher_is_better"])
-    for k in ("workload", "image", "batch_per_gpu", "pre_nms", "rois", "detections", "model"):
+    for k in ("workload", "name", "image", "batch_per_gpu", "pre_nms", "rois", "detections", "model"):
         assert d["config"][k] == gpu["config"][k]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_roialign_workload_line_and_reference_arm():
+    """configs[4] through bench.py: the committed GPU line carries the three byte models side by side, and the reference arm
+    (oracle crop_and_resize on the host cores) prints the same metric."""
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2a_bench_roialign.json")))
+    assert BASE_KEYS | {"clocks", "gpu_launches", "roofline", "sweep"} <= set(d)
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    assert r["frac_dram"] is not None and r["frac_survey_model"] >= r["frac"]          # the survey model charges untouched pixels too
+    assert len(d["sweep"]) == 30 and all(x["bytes_touched"] <= x["bytes_survey"] for x in d["sweep"])
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "roialign", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    ref = json.loads([l for l in p.stdout.splitlines() if l.strip()][0])
+    assert ref["impl"] == "reference" and (ref["metric"], ref["unit"]) == (d["metric"], d["unit"]) and ref["cpu_baseline"]["cores"] >= 1
