@@ -39,7 +39,7 @@ typedef std::vector<std::function<int(mrcnn_ctx*)>> Graph;
 struct DenseModel {
   WeightSet ws[3];
   std::map<std::string, Buf> bufs;
-  std::map<int, std::shared_ptr<Graph>> g_backbone;       // keyed by batch
+  std::map<int, std::shared_ptr<Graph>> g_backbone;       // keyed by 2 * batch + parity (output set, see build_backbone)
   std::map<int64_t, std::shared_ptr<Graph>> g_cls, g_mask; // keyed by total rois / detections
   std::map<int64_t, std::shared_ptr<ConvPlan>> mask_last;  // deconv + fused mask tail (output pointer patched per call)
   int lvl_h[5] = {0}, lvl_w[5] = {0};
@@ -53,6 +53,8 @@ struct DenseModel {
   StreamSlot slot[2];
   cudaStream_t copy_stream = nullptr;   // H2D of batch i+1 runs here while batch i computes on ctx->stream
   cudaStream_t copy_out_stream = nullptr;   // D2H of batch i runs here while batch i+1 computes
+  cudaStream_t heads_stream = nullptr;      // proposal .. mask section of batch i runs here under the backbone of batch i+1
+  cudaEvent_t backbone_done[2] = {nullptr, nullptr};
   uint64_t submitted = 0, completed = 0;
 };
 
@@ -124,6 +126,8 @@ void dense_destroy(mrcnn_ctx* ctx) {
   }
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->copy_out_stream) cudaStreamDestroy(m->copy_out_stream);
+  if (m->heads_stream) cudaStreamDestroy(m->heads_stream);
+  for (int i = 0; i < 2; ++i) if (m->backbone_done[i]) cudaEventDestroy(m->backbone_done[i]);
   delete m;
   ctx->dense = nullptr;
 }
@@ -207,7 +211,7 @@ static inline int grid1d(int64_t total, int threads) { return (int)((total + thr
 // ------------------------------------------------------------------------------
 // main model: ResNet + FPN + RPN
 // ------------------------------------------------------------------------------
-static int build_backbone(mrcnn_ctx* ctx, int B, std::shared_ptr<Graph>* out_graph) {
+static int build_backbone(mrcnn_ctx* ctx, int B, int parity, std::shared_ptr<Graph>* out_graph) {
   DenseModel* m = model_of(ctx);
   MRCNN_REQUIRE(ctx, m->ws[0].loaded, "main model weights not loaded (mrcnn_set_weights(ctx, 0, ...) / main_model_path)");
   const mrcnn_config& cfg = ctx->cfg;
@@ -320,7 +324,11 @@ static int build_backbone(mrcnn_ctx* ctx, int B, std::shared_ptr<Graph>* out_gra
   for (int l = 0; l < 5; ++l) { m->lvl_h[l] = lh[l]; m->lvl_w[l] = lw[l]; }
   __half *mrg[4], *p[5];
   const char* mn[4] = {"m2", "m3", "m4", "m5"};
-  const char* pn[5] = {"p2", "p3", "p4", "p5", "p6"};
+  // what the stage AFTER the backbone reads (P2..P5, RPN outputs) exists twice: in the streaming API the backbone of
+  // batch i + 1 runs while the proposal / heads section of batch i still reads its set (parity = batch & 1)
+  const char* pn0[5] = {"p2", "p3", "p4", "p5", "p6"};
+  const char* pn1[5] = {"p2#1", "p3#1", "p4#1", "p5#1", "p6"};
+  const char* const* pn = parity ? pn1 : pn0;
   for (int l = 0; l < 4; ++l) TRY(get_buf(ctx, mn[l], elems(lh[l], lw[l], 256) * 2, (void**)&mrg[l]));
   for (int l = 0; l < 5; ++l) TRY(get_buf(ctx, pn[l], elems(lh[l], lw[l], 256) * 2, (void**)&p[l]));
   const char* lat[4] = {"fpn.c2p2", "fpn.c3p3", "fpn.c4p4", "fpn.c5p5"};
@@ -354,8 +362,8 @@ static int build_backbone(mrcnn_ctx* ctx, int B, std::shared_ptr<Graph>* out_gra
   __half* shared; float *head, *probs, *deltas;
   TRY(get_buf(ctx, "rpn_shared", elems(lh[0], lw[0], 512) * 2, (void**)&shared));
   TRY(get_buf(ctx, "rpn_head", elems(lh[0], lw[0], 24) * 4, (void**)&head));
-  TRY(get_buf(ctx, "rpn_probs", (size_t)MB * N * 2 * 4, (void**)&probs));
-  TRY(get_buf(ctx, "rpn_deltas", (size_t)MB * N * 4 * 4, (void**)&deltas));
+  TRY(get_buf(ctx, parity ? "rpn_probs#1" : "rpn_probs", (size_t)MB * N * 2 * 4, (void**)&probs));
+  TRY(get_buf(ctx, parity ? "rpn_deltas#1" : "rpn_deltas", (size_t)MB * N * 4 * 4, (void**)&deltas));
   int64_t off = 0;
   for (int l = 0; l < 5; ++l) {
     ConvArgs A;
@@ -383,14 +391,14 @@ static int run_graph(mrcnn_ctx* ctx, const Graph& g) {
   return MRCNN_OK;
 }
 
-static int backbone_graph(mrcnn_ctx* ctx, int B, std::shared_ptr<Graph>* g) {
+static int backbone_graph(mrcnn_ctx* ctx, int B, std::shared_ptr<Graph>* g, int parity = 0) {
   DenseModel* m = model_of(ctx);
-  auto it = m->g_backbone.find(B);
+  auto it = m->g_backbone.find(2 * B + parity);
   if (it == m->g_backbone.end()) {
     std::shared_ptr<Graph> ng;
-    TRY(build_backbone(ctx, B, &ng));
+    TRY(build_backbone(ctx, B, parity, &ng));
     // building may have (re)allocated buffers and dropped the cache: insert afterwards
-    m->g_backbone[B] = ng;
+    m->g_backbone[2 * B + parity] = ng;
     *g = ng;
   } else *g = it->second;
   return MRCNN_OK;
@@ -584,7 +592,19 @@ static void stage_collect(mrcnn_ctx* ctx) {
 // ------------------------------------------------------------------------------
 // The fused pipeline.  All pointers are device pointers.
 // ------------------------------------------------------------------------------
-static int predict_device(mrcnn_ctx* ctx, int B, const uint8_t* d_rgb, float* d_det, float* d_masks) {
+// Restores the context's stream when a function that switched it returns (also on the error paths).
+struct StreamGuard {
+  mrcnn_ctx* ctx; cudaStream_t saved;
+  explicit StreamGuard(mrcnn_ctx* c) : ctx(c), saved(c->stream) {}
+  ~StreamGuard() { ctx->stream = saved; }
+};
+
+// parity: which set of backbone outputs (P2..P5, RPN outputs) this batch uses.  heads: stream for everything after
+// the backbone (nullptr: the context's stream) -- the streaming API runs that section of batch i beside the backbone
+// of batch i + 1; it holds the latency-bound kernels (top-k, sort, NMS resolves: a few dozen CTAs) whose idle SMs the
+// other batch's convolutions fill.
+static int predict_device(mrcnn_ctx* ctx, int B, const uint8_t* d_rgb, float* d_det, float* d_masks,
+                          int parity = 0, cudaStream_t heads = nullptr) {
   DenseModel* m = model_of(ctx);
   const mrcnn_config& cfg = ctx->cfg;
   MRCNN_REQUIRE(ctx, B >= 1, "predict: batch must be >= 1");
@@ -600,13 +620,13 @@ static int predict_device(mrcnn_ctx* ctx, int B, const uint8_t* d_rgb, float* d_
     // so the check at the end of the pass must come after the last reservation
     TRY(get_buf(ctx, "rois", (size_t)MB * R * 4 * 4, (void**)&rois));
     TRY(get_buf(ctx, "cls6", (size_t)MB * R * 6 * 4, (void**)&cls6));
-    TRY(backbone_graph(ctx, B, &gb));
+    TRY(backbone_graph(ctx, B, &gb, parity));
     TRY(cls_graph(ctx, (int64_t)B * R, &gc));
     TRY(mask_graph(ctx, (int64_t)B * D, &gm));
-    if (m->g_backbone.count(B) && m->g_cls.count((int64_t)B * R) && m->g_mask.count((int64_t)B * D) &&
+    if (m->g_backbone.count(2 * B + parity) && m->g_cls.count((int64_t)B * R) && m->g_mask.count((int64_t)B * D) &&
         m->mask_last.count((int64_t)B * D)) break;
   }
-  MRCNN_REQUIRE(ctx, m->g_backbone.count(B) && m->g_cls.count((int64_t)B * R) && m->g_mask.count((int64_t)B * D) &&
+  MRCNN_REQUIRE(ctx, m->g_backbone.count(2 * B + parity) && m->g_cls.count((int64_t)B * R) && m->g_mask.count((int64_t)B * D) &&
                 m->mask_last.count((int64_t)B * D), "predict: internal error, graphs invalidated while building");
   MRCNN_REQUIRE(ctx, ctx->d_anchors && ctx->num_anchors == m->n_anchors, "predict: anchors not loaded or anchor count does not match the image size");
   m->rgb = d_rgb;     // consumed by the pre-processing closure
@@ -614,12 +634,20 @@ static int predict_device(mrcnn_ctx* ctx, int B, const uint8_t* d_rgb, float* d_
   stage_mark(ctx, "start");
   TRY(run_graph(ctx, *gb));
   stage_mark(ctx, "Backbone+FPN+RPN");
-  const float* probs = (const float*)m->bufs["rpn_probs"].p;
-  const float* deltas = (const float*)m->bufs["rpn_deltas"].p;
+  StreamGuard guard(ctx);
+  if (heads) {
+    if (!m->backbone_done[parity]) MRCNN_CUDA_TRY(ctx, cudaEventCreateWithFlags(&m->backbone_done[parity], cudaEventDisableTiming));
+    MRCNN_CUDA_TRY(ctx, cudaEventRecord(m->backbone_done[parity], ctx->stream));
+    MRCNN_CUDA_TRY(ctx, cudaStreamWaitEvent(heads, m->backbone_done[parity], 0));
+    ctx->stream = heads;                 // every launch below goes to the heads stream (restored by the guard)
+  }
+  const float* probs = (const float*)m->bufs[parity ? "rpn_probs#1" : "rpn_probs"].p;
+  const float* deltas = (const float*)m->bufs[parity ? "rpn_deltas#1" : "rpn_deltas"].p;
   TRY(proposal_run(ctx, B, m->n_anchors, probs, deltas, rois, nullptr, nullptr));
   stage_mark(ctx, "Proposal-Eval");
-  const __half* fm[4] = {(const __half*)m->bufs["p2"].p, (const __half*)m->bufs["p3"].p, (const __half*)m->bufs["p4"].p,
-                         (const __half*)m->bufs["p5"].p};
+  const char* pnames[2][4] = {{"p2", "p3", "p4", "p5"}, {"p2#1", "p3#1", "p4#1", "p5#1"}};
+  const __half* fm[4];
+  for (int l = 0; l < 4; ++l) fm[l] = (const __half*)m->bufs[pnames[parity][l]].p;
   int32_t hw[8];
   for (int l = 0; l < 4; ++l) { hw[2 * l] = m->lvl_h[l]; hw[2 * l + 1] = m->lvl_w[l]; }
   TRY(roialign_nhwc_f16_run(ctx, B, rois, 4, R, fm, hw, 256, P7, (__half*)m->bufs["pooled_cls"].p, nullptr));
@@ -716,7 +744,8 @@ static int allgather_reserve(mrcnn_ctx* ctx, int batch_local) {
 
 // predict on this rank's images, then the one exchange step of the path: a single all-gather of the packed rows over
 // NVLink.  Device pointers; buffers reserved by allgather_reserve.
-static int predict_allgather_device(mrcnn_ctx* ctx, int batch_local, const uint8_t* drgb, float* ddet_all, float* dmask_all) {
+static int predict_allgather_device(mrcnn_ctx* ctx, int batch_local, const uint8_t* drgb, float* ddet_all, float* dmask_all,
+                                    int parity = 0, cudaStream_t heads = nullptr) {
   DenseModel* m = model_of(ctx);
   const mrcnn_config& cfg = ctx->cfg;
   const int D = cfg.max_detections, S = 2 * cfg.pool_size_mask;
@@ -724,7 +753,9 @@ static int predict_allgather_device(mrcnn_ctx* ctx, int batch_local, const uint8
   const int total = batch_local * ctx->nranks;
   float* ldet = (float*)m->bufs["ag_det"].p; float* lmask = (float*)m->bufs["ag_mask"].p;
   float* send = (float*)m->bufs["ag_send"].p; float* recv = (float*)m->bufs["ag_recv"].p;
-  TRY(predict_device(ctx, batch_local, drgb, ldet, lmask));
+  TRY(predict_device(ctx, batch_local, drgb, ldet, lmask, parity, heads));
+  StreamGuard guard(ctx);
+  if (heads) ctx->stream = heads;        // the exchange follows the heads section on its stream: under the next batch's backbone
   {
     ProfScope ps(ctx, PROF_GLUE, (double)row * 4.0 * (batch_local * 2 + total * 2));
     pack_rows_kernel<<<dim3(32, batch_local), 256, 0, ctx->stream>>>(ldet, lmask, n_det, n_mask, send);
@@ -848,6 +879,7 @@ MRCNN_API int mrcnn_backbone_eval(mrcnn_ctx* ctx, int batch, const uint8_t* rgb,
 MRCNN_API int mrcnn_predict(mrcnn_ctx* ctx, int batch, const uint8_t* rgb, float* detections, float* masks) {
   if (!ctx) return MRCNN_EINVAL;
   MRCNN_REQUIRE(ctx, rgb && detections && masks && batch >= 1, "predict: bad argument");
+  MRCNN_REQUIRE(ctx, mrcnn_predict_in_flight(ctx) == 0, "predict: streamed batches are in flight; call mrcnn_predict_wait first");
   cudaSetDevice(ctx->device);
   const mrcnn_config& cfg = ctx->cfg;
   const int D = cfg.max_detections, S = 2 * cfg.pool_size_mask;
@@ -865,6 +897,7 @@ MRCNN_API int mrcnn_predict_allgather(mrcnn_ctx* ctx, int batch_local, const uin
   if (!ctx) return MRCNN_EINVAL;
   MRCNN_REQUIRE(ctx, rgb && detections_all && masks_all && batch_local >= 1, "predict_allgather: bad argument");
   MRCNN_REQUIRE(ctx, ctx->nccl_comm, "predict_allgather: call mrcnn_comm_init first");
+  MRCNN_REQUIRE(ctx, mrcnn_predict_in_flight(ctx) == 0, "predict_allgather: streamed batches are in flight; call mrcnn_predict_wait first");
   cudaSetDevice(ctx->device);
   const mrcnn_config& cfg = ctx->cfg;
   const int D = cfg.max_detections, S = 2 * cfg.pool_size_mask;
@@ -930,17 +963,28 @@ MRCNN_API int mrcnn_predict_submit(mrcnn_ctx* ctx, int batch, const uint8_t* rgb
   }
   float* ddet = det_host ? (float*)m->bufs[nm_det[k]].p : detections;
   float* dmask = mask_host ? (float*)m->bufs[nm_mask[k]].p : masks;
-  if (gather) TRY(predict_allgather_device(ctx, batch, drgb, ddet, dmask));
-  else TRY(predict_device(ctx, batch, drgb, ddet, dmask));
+  // two-stage software pipeline: the backbone of this batch runs on the context's stream right behind the previous
+  // batch's backbone, everything after it on the heads stream behind the previous batch's heads
+  // (MRCNN_STREAM_HEADS=0: one stream, as the blocking call)
+  static int use_heads = -1;
+  if (use_heads < 0) { const char* e = getenv("MRCNN_STREAM_HEADS"); use_heads = e ? atoi(e) != 0 : 1; }
+  cudaStream_t heads = nullptr;
+  if (use_heads) {
+    if (!m->heads_stream) MRCNN_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&m->heads_stream, cudaStreamNonBlocking));
+    heads = m->heads_stream;
+  }
+  cudaStream_t tail = heads ? heads : ctx->stream;
+  if (gather) TRY(predict_allgather_device(ctx, batch, drgb, ddet, dmask, k, heads));
+  else TRY(predict_device(ctx, batch, drgb, ddet, dmask, k, heads));
   if (det_host || mask_host) {
     // results leave on their own stream, under the compute of the next batch (which writes the other slot's mirrors)
-    MRCNN_CUDA_TRY(ctx, cudaEventRecord(sl.computed, ctx->stream));
+    MRCNN_CUDA_TRY(ctx, cudaEventRecord(sl.computed, tail));
     MRCNN_CUDA_TRY(ctx, cudaStreamWaitEvent(m->copy_out_stream, sl.computed, 0));
     if (det_host) MRCNN_CUDA_TRY(ctx, cudaMemcpyAsync(detections, ddet, det_bytes, cudaMemcpyDeviceToHost, m->copy_out_stream));
     if (mask_host) MRCNN_CUDA_TRY(ctx, cudaMemcpyAsync(masks, dmask, mask_bytes, cudaMemcpyDeviceToHost, m->copy_out_stream));
     MRCNN_CUDA_TRY(ctx, cudaEventRecord(sl.done, m->copy_out_stream));
   } else {
-    MRCNN_CUDA_TRY(ctx, cudaEventRecord(sl.done, ctx->stream));
+    MRCNN_CUDA_TRY(ctx, cudaEventRecord(sl.done, tail));
   }
   m->submitted++;
   return MRCNN_OK;
