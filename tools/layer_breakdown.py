@@ -18,6 +18,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 B, IMG, R, D = 8, 1024, 1000, 100
 
 
+ONE_TERM_MASKS = "--one-term-masks" in sys.argv      # launch lists taken with precise_masks = 0 (round 1)
+
+
 def plan(architecture=101):
     """[(class, M, N, K_useful, algorithmic bytes)] of every conv_gemm launch of one step, in launch order.
     Algorithmic bytes = every operand once: input pixels the layer needs (fp16), weights, output, residual."""
@@ -54,15 +57,24 @@ def plan(architecture=101):
     add("classifier conv1 7x7 (gemm)", B * R, 1024, 49 * 256, 49 * 256)
     add("classifier conv2 1x1", B * R, 1024, 1024, 1024)
     add("classifier logits+boxes", B * R, 405, 1024, 1024, out_bytes=4 * B * R * 408)
-    for _ in range(4):
-        add("mask conv 3x3", B * D * 14 * 14, 256, 9 * 256, 256)
     m = B * D * 14 * 14
-    add("mask deconv 2x2 + class plane", m, 1024, 256, 256, out_bytes=4 * m * 4)     # only the selected class plane leaves, fp32
+    if ONE_TERM_MASKS:
+        for _ in range(4):
+            add("mask conv 3x3", m, 256, 9 * 256, 256)
+        add("mask deconv 2x2 + class plane", m, 1024, 256, 256, out_bytes=4 * m * 4)     # only the selected class plane leaves, fp32
+    else:
+        # library default (precise_masks = 1): activations leave every layer as (hi, lo) fp16 pairs = 512 channels, and the
+        # layers that consume them run with K doubled (hi * w + lo * w); the pooled input of conv1 is exact fp16 (K = 9 * 256)
+        add("mask conv 3x3", m, 256, 9 * 256, 256, out_bytes=2 * m * 512)
+        for _ in range(3):
+            add("mask conv 3x3", m, 256, 9 * 512, 512, out_bytes=2 * m * 512)
+        add("mask deconv 2x2 + class plane", m, 1024, 512, 512, out_bytes=4 * m * 4)
     return L
 
 
 def main():
-    path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "r1w_pipeline_launches_warm.csv")
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    path = args[0] if args else os.path.join(ROOT, "profiles", "r1w_pipeline_launches_warm.csv")
     txt = open(path).read()
     txt = txt[txt.index('"ID"'):]
     by = collections.OrderedDict()
