@@ -107,17 +107,30 @@ def lib():
     return l
 
 
-def ptr(x):
-    """Raw address of a numpy array (host) or a torch tensor (host or cuda); None -> NULL."""
+_NP_NAMES = {"uint8": "uint8", "float32": "float32", "float16": "float16", "int32": "int32", "float64": "float64"}
+
+
+def ptr(x, dtype=None, count=None):
+    """Raw address of a numpy array (host) or a torch tensor (host or cuda); None -> NULL.
+    dtype (a numpy dtype name, e.g. "float32") and count (minimum number of elements) are checked when given: the C ABI
+    takes plain pointers, so a buffer of the wrong element type or size would be reinterpreted or overrun silently."""
     if x is None:
         return None
     if hasattr(x, "data_ptr"):            # torch.Tensor
         if not x.is_contiguous():
             raise MaskRCNNError(EINVAL, "tensor must be contiguous")
+        if dtype is not None and str(x.dtype).replace("torch.", "") != _NP_NAMES[dtype]:
+            raise MaskRCNNError(EINVAL, f"tensor must be {dtype}, got {x.dtype}")
+        if count is not None and x.numel() < count:
+            raise MaskRCNNError(EINVAL, f"tensor has {x.numel()} elements, {count} needed")
         return C.c_void_p(x.data_ptr())
     if hasattr(x, "ctypes"):              # numpy.ndarray
         if not x.flags["C_CONTIGUOUS"]:
             raise MaskRCNNError(EINVAL, "array must be C-contiguous")
+        if dtype is not None and x.dtype.name != dtype:
+            raise MaskRCNNError(EINVAL, f"array must be {dtype}, got {x.dtype}")
+        if count is not None and x.size < count:
+            raise MaskRCNNError(EINVAL, f"array has {x.size} elements, {count} needed")
         return C.c_void_p(x.ctypes.data)
     if isinstance(x, int):
         return C.c_void_p(x)

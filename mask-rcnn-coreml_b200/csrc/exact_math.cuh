@@ -52,21 +52,27 @@ struct RectD {
 };
 
 __device__ __forceinline__ RectD make_rect(float4 b) {
+  // CGRect(x: x1, y: y1, width: x2 - x1, height: y2 - y1) (Utils.swift:222-231); CGRect's width / height / minX / maxX are
+  // those of the STANDARDISED rectangle: |w|, |h|, min and max edge.  Boxes with x2 >= x1, y2 >= y1 (every box the
+  // layers decode themselves) give exactly the values of the plain formulas.
   RectD r;
   double y1 = (double)b.x, x1 = (double)b.y, y2 = (double)b.z, x2 = (double)b.w;
   double w = __dsub_rn(x2, x1), h = __dsub_rn(y2, y1);
-  r.x1 = x1; r.y1 = y1;
-  r.maxx = __dadd_rn(x1, w);
-  r.maxy = __dadd_rn(y1, h);
-  r.area = __dmul_rn(w, h);
+  const double xe = __dadd_rn(x1, w), ye = __dadd_rn(y1, h);
+  r.x1 = w >= 0.0 ? x1 : xe; r.maxx = w >= 0.0 ? xe : x1;
+  r.y1 = h >= 0.0 ? y1 : ye; r.maxy = h >= 0.0 ? ye : y1;
+  r.area = fabs(__dmul_rn(w, h));
   return r;
 }
 
 __device__ __forceinline__ bool box_selectable(float4 b) {
-  // Utils.swift:195: anchorA.width > 0 && anchorA.height > 0 (Double)
+  // Utils.swift:195: anchorA.width > 0 && anchorA.height > 0 (Double; width / height of the standardised rect = |w|, |h|)
   double w = __dsub_rn((double)b.w, (double)b.y), h = __dsub_rn((double)b.z, (double)b.x);
-  return (w > 0.0) && (h > 0.0);
+  return (fabs(w) > 0.0) && (fabs(h) > 0.0);
 }
+
+// x2 >= x1 and y2 >= y1: the box is its own standardised rectangle (the fp32 fast path of nms_mask_kernel needs that)
+__device__ __forceinline__ bool box_ordered(float4 b) { return b.w >= b.y && b.z >= b.x; }
 
 // Utils.swift:232-246 IOU: Double math, quotient rounded to Float.
 __device__ __forceinline__ float iou_rect(const RectD& a, const RectD& b) {

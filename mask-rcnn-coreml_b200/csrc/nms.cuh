@@ -30,7 +30,7 @@ nms_mask_kernel(const float4* __restrict__ boxes, const float* __restrict__ cls,
   const float* c = cls ? cls + (size_t)img * stride_boxes : nullptr;
 
   __shared__ RectD col_rect[NMS_TILE];
-  __shared__ float4 col_f[NMS_TILE];      // (x1, y1, ub(maxx), ub(maxy)) in fp32, upper bounds rounded up
+  __shared__ float4 col_f[NMS_TILE];      // (lb(minx), lb(miny), ub(maxx), ub(maxy)) in fp32: lower bounds rounded down, upper up
   __shared__ float col_cls[NMS_TILE];
   __shared__ float4 col_box[NMS_TILE];    // (y1, x1, y2, x2) as given
   __shared__ float col_area[NMS_TILE];    // fp32 area estimate (sign-exact: zero / negative exactly when the fp64 area is)
@@ -40,19 +40,20 @@ nms_mask_kernel(const float4* __restrict__ boxes, const float* __restrict__ cls,
     const RectD rc = make_rect(b[cj]);
     col_rect[t] = rc;
     col_box[t] = b[cj];
-    col_area[t] = (b[cj].w - b[cj].y) * (b[cj].z - b[cj].x);
-    col_f[t] = make_float4(b[cj].y, b[cj].x, __double2float_ru(rc.maxx), __double2float_ru(rc.maxy));
+    // inverted boxes (caller-supplied anchors / rois only) never take the fp32 path: area estimate 0
+    col_area[t] = box_ordered(b[cj]) ? (b[cj].w - b[cj].y) * (b[cj].z - b[cj].x) : 0.0f;
+    col_f[t] = make_float4(__double2float_rd(rc.x1), __double2float_rd(rc.y1), __double2float_ru(rc.maxx), __double2float_ru(rc.maxy));
     col_cls[t] = c ? c[cj] : 0.0f;
   }
   __syncthreads();
   const int i = rb * NMS_TILE + t;
   if (i >= n) return;
   const RectD me = make_rect(b[i]);
-  const float mx1 = b[i].y, my1 = b[i].x;
+  const float mx1 = __double2float_rd(me.x1), my1 = __double2float_rd(me.y1);      // lower bounds of the min edges
   const float mubx = __double2float_ru(me.maxx), muby = __double2float_ru(me.maxy);
   const float mycls = c ? c[i] : 0.0f;
   const float4 mb = b[i];
-  const float marea = (mb.w - mb.y) * (mb.z - mb.x);
+  const float marea = box_ordered(mb) ? (mb.w - mb.y) * (mb.z - mb.x) : 0.0f;
   const int ncol = min(NMS_TILE, n - cb * NMS_TILE);
   const bool prefilter = thr >= 0.0f;     // IoU of a disjoint pair is exactly 0, never > a non-negative threshold
   unsigned long long bits = 0ull;

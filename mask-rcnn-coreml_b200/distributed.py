@@ -65,6 +65,7 @@ class DistributedMaskRCNN:
             if unique_id is None:
                 raise _cabi.MaskRCNNError(_cabi.EINVAL, "unique_id (128 bytes from nccl_unique_id() on rank 0) is required")
             check(model.ctx.handle, lib().mrcnn_comm_init(model.ctx.handle, bytes(unique_id), rank, world))
+            model.ctx.nranks = world          # MaskRCNN.submit(allgather=True) sizes its output checks with it
 
     @staticmethod
     def nccl_unique_id():

@@ -110,8 +110,14 @@ class MaskRCNN:
             detections = np.empty((b, self.D, 6), np.float32)
         if masks is None:
             masks = np.empty((b, self.D, self.S, self.S), np.float32)
-        check(self.ctx.handle, lib().mrcnn_predict(self.ctx.handle, b, ptr(images), ptr(detections), ptr(masks)))
+        check(self.ctx.handle, lib().mrcnn_predict(self.ctx.handle, b, *self._io(b, images, detections, masks)))
         return detections, masks
+
+    def _io(self, b, images, detections, masks, total=None):
+        """Checked pointers of the model's input / outputs (element type and size; see _cabi.ptr)."""
+        t = b if total is None else total
+        return (ptr(images, "uint8", b * self.shape[0] * self.shape[1] * 3), ptr(detections, "float32", t * self.D * 6),
+                ptr(masks, "float32", t * self.D * self.S * self.S))
 
     # ---- streaming: two batches in flight (mrcnn_predict_submit / mrcnn_predict_wait) ----
     def submit(self, images, detections, masks, allgather=False):
@@ -122,7 +128,8 @@ class MaskRCNN:
         if tuple(images.shape[1:]) != self.shape:
             raise _cabi.MaskRCNNError(_cabi.EINVAL, f"images must be [B,{self.shape[0]},{self.shape[1]},3] uint8")
         flags = 1 if allgather else 0          # MRCNN_SUBMIT_ALLGATHER
-        check(self.ctx.handle, lib().mrcnn_predict_submit(self.ctx.handle, b, ptr(images), ptr(detections), ptr(masks), flags))
+        total = b * max(int(getattr(self.ctx, "nranks", 1)), 1) if allgather else b
+        check(self.ctx.handle, lib().mrcnn_predict_submit(self.ctx.handle, b, *self._io(b, images, detections, masks, total), flags))
 
     def wait(self):
         """Blocks until the oldest submitted batch is complete (outputs are in the buffers given to submit)."""
@@ -134,20 +141,42 @@ class MaskRCNN:
 
     def prediction_stream(self, batches):
         """Iterator of image batches -> iterator of (detections, masks), in order, keeping two batches in flight:
-        the loop of EvaluateCommand.swift:166-194 with the copies off the critical path."""
-        pending = []
-        for images in batches:
-            b = images.shape[0]
-            det = np.empty((b, self.D, 6), np.float32)
-            msk = np.empty((b, self.D, self.S, self.S), np.float32)
-            if len(pending) == 2:
+        the loop of EvaluateCommand.swift:166-194 with the copies off the critical path.
+        Outputs land in PINNED host slots (three, reused) and are yielded as copies: with pageable buffers the
+        device-to-host copy would block submit() until the batch is computed, and the overlap would be lost.  Input
+        batches are used as given -- pin them (torch .pin_memory()) for an asynchronous upload.  Closing the generator
+        early waits for the batches still in flight, so their buffers are not released under a running copy."""
+        import torch
+        slots, pending, n = [], [], 0
+        try:
+            for images in batches:
+                b = images.shape[0]
+                if len(pending) == 2:
+                    self.wait()
+                    _, det, msk = pending.pop(0)
+                    yield det.numpy().copy(), msk.numpy().copy()
+                k = n % 3
+                n += 1
+                if len(slots) <= k or slots[k][0].shape[0] != b:
+                    slot = (torch.empty((b, self.D, 6), dtype=torch.float32).pin_memory(),
+                            torch.empty((b, self.D, self.S, self.S), dtype=torch.float32).pin_memory())
+                    if len(slots) <= k:
+                        slots.append(slot)
+                    else:
+                        slots[k] = slot
+                det, msk = slots[k]
+                self.submit(images, det, msk)
+                pending.append((images, det, msk))      # keeps the input alive until its wait
+            while pending:
                 self.wait()
-                yield pending.pop(0)[1:]
-            self.submit(images, det, msk)
-            pending.append((images, det, msk))      # keeps the input alive until its wait
-        while pending:
-            self.wait()
-            yield pending.pop(0)[1:]
+                _, det, msk = pending.pop(0)
+                yield det.numpy().copy(), msk.numpy().copy()
+        finally:
+            while self.in_flight:                       # generator closed early (or an error): drain what was submitted
+                try:
+                    self.wait()
+                except _cabi.MaskRCNNError:
+                    break
 
     def prediction(self, image):
         """One image -> {"detections": (D,6), "mask": (D,S,S)} like MaskRCNNOutput."""
@@ -164,7 +193,10 @@ class MaskRCNN:
         h, w = image.shape[:2]
         if out is None:
             out = np.empty(self.shape, np.uint8)
-        check(self.ctx.handle, lib().mrcnn_letterbox_eval(self.ctx.handle, ptr(image), h, w, ptr(out)))
+        if image.ndim != 3 or image.shape[2] != 3:
+            raise _cabi.MaskRCNNError(_cabi.EINVAL, "letterbox: image must be (H, W, 3) uint8")
+        check(self.ctx.handle, lib().mrcnn_letterbox_eval(self.ctx.handle, ptr(image, "uint8", h * w * 3), h, w,
+                                                          ptr(out, "uint8", self.shape[0] * self.shape[1] * 3)))
         return out
 
     def unletterbox(self, rows, src_h, src_w):

@@ -130,21 +130,27 @@ ORC_API void orc_clip(float* v, int count) {
 /* ------------------------------------------------------------------------- */
 /* Utils.swift:222-229 CGRect(anchorDatum:) and Utils.swift:232-246 IOU.      */
 /* CGFloat == Double on 64-bit Darwin. Boxes are (y1,x1,y2,x2) fp32.          */
-/* After clip() width/height are >= 0, so CGRect standardisation is a no-op.   */
+/* CGRect.width / height / minX / maxX are those of the STANDARDISED rectangle  */
+/* (|w|, |h|, min / max edge); for the boxes the layers decode themselves       */
+/* (x2 >= x1, y2 >= y1) that is the identity.                                   */
 /* ------------------------------------------------------------------------- */
 ORC_API float orc_iou(const float* a, const float* b) {
   double ay1 = a[0], ax1 = a[1], ay2 = a[2], ax2 = a[3];
   double by1 = b[0], bx1 = b[1], by2 = b[2], bx2 = b[3];
   double aw = ax2 - ax1, ah = ay2 - ay1;
   double bw = bx2 - bx1, bh = by2 - by1;
-  double areaA = aw * ah;
+  double areaA = fabs(aw * ah);
   if (areaA <= 0) return 0.0f;
-  double areaB = bw * bh;
+  double areaB = fabs(bw * bh);
   if (areaB <= 0) return 0.0f;
-  double aMaxX = ax1 + aw, aMaxY = ay1 + ah;
-  double bMaxX = bx1 + bw, bMaxY = by1 + bh;
-  double iMinX = ax1 > bx1 ? ax1 : bx1;
-  double iMinY = ay1 > by1 ? ay1 : by1;
+  double aEndX = ax1 + aw, aEndY = ay1 + ah;
+  double bEndX = bx1 + bw, bEndY = by1 + bh;
+  double aMinX = aw >= 0 ? ax1 : aEndX, aMaxX = aw >= 0 ? aEndX : ax1;
+  double aMinY = ah >= 0 ? ay1 : aEndY, aMaxY = ah >= 0 ? aEndY : ay1;
+  double bMinX = bw >= 0 ? bx1 : bEndX, bMaxX = bw >= 0 ? bEndX : bx1;
+  double bMinY = bh >= 0 ? by1 : bEndY, bMaxY = bh >= 0 ? bEndY : by1;
+  double iMinX = aMinX > bMinX ? aMinX : bMinX;
+  double iMinY = aMinY > bMinY ? aMinY : bMinY;
   double iMaxX = aMaxX < bMaxX ? aMaxX : bMaxX;
   double iMaxY = aMaxY < bMaxY ? aMaxY : bMaxY;
   double ih = iMaxY - iMinY;
@@ -170,7 +176,7 @@ ORC_API int orc_nms(const float* boxes, const int* indices, int n_idx,
     const float* A = boxes + (size_t)index * 4;
     double w = (double)A[3] - (double)A[1];
     double h = (double)A[2] - (double)A[0];
-    int keep = (w > 0) && (h > 0);                    /* :195 */
+    int keep = (fabs(w) > 0) && (fabs(h) > 0);        /* :195, CGRect.width / height = |w|, |h| */
     if (keep) {
       for (int s = 0; s < count; ++s) {              /* :200 */
         const float* B = boxes + (size_t)selected[s] * 4;

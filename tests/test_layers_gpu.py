@@ -415,3 +415,26 @@ def test_detection_randomised_configs(pkg, orc, seed, r, ncls, maxdet):
     np.testing.assert_array_equal(keep[0], k0)
     np.testing.assert_array_equal(out[0], o0)
     c.close()
+
+
+def test_detection_layer_inverted_rois_follow_cgrect_standardisation(pkg, ctx, orc):
+    """DetectionLayer on caller-supplied rois with x2 < x1 / y2 < y1: the decoded boxes stay inverted, and the NMS treats
+    them as CGRect does (|w|, |h|, min / max edges, Utils.swift:194-246) -- the fp32 fast path of the bitmask kernel
+    must not be taken for them.  Bit-exact against the oracle."""
+    rng = np.random.default_rng(12)
+    r = 600
+    rois = pkg.synth.random_rois(r, 33, min_px=40, max_px=300).copy()
+    inv = rng.random(r) < 0.35
+    rois[inv] = rois[inv][:, [2, 3, 0, 1]]                          # both axes inverted: valid level, negative w and h
+    pr, bb = pkg.synth.classifier_outputs(r, 34)
+    cls = orc.classifier_select(pr, bb)
+    cls[:, :4] *= np.float32(0.1)                                   # small refinements: the inversion survives the decode
+    cls[:, 4] = np.where(cls[:, 4] > 0, 1 + (cls[:, 4] % 3), 0)     # few classes -> plenty of same-class overlaps
+    det = np.zeros((1, 100, 6), np.float32); keep = np.zeros((1, 100), np.int32); cnt = np.zeros(1, np.int32)
+    pkg.DetectionLayer(context=ctx).evaluate([rois[None], cls[None]], [det], keep, cnt)
+    d0, k0, n0 = orc.detection(rois, cls)
+    assert cnt[0] == n0 and n0 > 5
+    np.testing.assert_array_equal(keep[0, :n0], k0[:n0])
+    np.testing.assert_array_equal(det[0], d0)
+    b = det[0, :n0, :4]
+    assert ((b[:, 2] < b[:, 0]) | (b[:, 3] < b[:, 1])).any()        # inverted boxes are among the detections

@@ -300,3 +300,26 @@ def test_proposal_at_the_baseline_sizes_with_the_reference_index_range(orc, m, s
     assert dcnt == len(didx) and dcnt > 0
     np.testing.assert_array_equal(dout, det)
     np.testing.assert_array_equal(np.array(didx, np.int32), dkeep[:dcnt])
+
+
+def test_nms_on_inverted_boxes_follows_cgrect_standardisation(orc):
+    """CGRect.width / height / minX / maxX are those of the standardised rectangle (Utils.swift:194-246 builds
+    CGRect(x: x1, y: y1, width: x2 - x1, height: y2 - y1) and reads them): a box given with x2 < x1 or y2 < y1 -- only
+    possible for caller-supplied anchors / rois, the layers' own decode keeps the order -- is selectable and overlaps
+    like its mirror image.  Both restatements agree, IoU values and keep lists, bit for bit."""
+    rng = np.random.default_rng(3)
+    n = 400
+    c = rng.uniform(0.2, 0.8, (n, 2)); e = rng.uniform(0.02, 0.2, (n, 2))
+    boxes = np.concatenate([c - e, c + e], 1).astype(np.float32)
+    flip_y, flip_x = rng.random(n) < 0.3, rng.random(n) < 0.3
+    boxes[flip_y] = boxes[flip_y][:, [2, 1, 0, 3]]
+    boxes[flip_x] = boxes[flip_x][:, [0, 3, 2, 1]]
+    boxes[7] = [0.3, 0.3, 0.3, 0.5]                                # zero height: never selectable
+    for i, j in rng.integers(0, n, (300, 2)):
+        assert orc.iou(boxes[i], boxes[j]) == float(lit.IOU(lit.CGRect(boxes[i]), lit.CGRect(boxes[j])))
+    a = boxes[3].copy(); a[[0, 2]] = a[[2, 0]]
+    assert orc.iou(a, boxes[3]) == 1.0 and orc.iou(boxes[3], a) == 1.0          # a box and its mirror image coincide
+    for thr in (0.3, 0.7):
+        keep = orc.nms(boxes, np.arange(n), thr, n)
+        assert keep.tolist() == lit.non_max_supression(boxes.reshape(-1), list(range(n)), thr, n)
+        assert 7 not in keep and (flip_y | flip_x)[keep].any()

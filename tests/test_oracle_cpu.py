@@ -208,3 +208,29 @@ def test_letterbox_known_answers(orc, pkg):
     back = np.zeros_like(boxes)
     assert pkg.lib().mrcnn_unletterbox_boxes(32, 64, 128, 128, pkg._cabi.ptr(boxes), 1, 6, pkg._cabi.ptr(back)) == 0
     np.testing.assert_allclose(back[0], [0, 0, 1, 1, 3, 0.9], atol=1e-6)
+
+
+def test_internal_fp16_roialign_is_bounded_against_the_fp32_layer(orc):
+    """The fused pipeline keeps feature maps and pooled features in fp16 (NHWC); the oracle variant that checks that
+    kernel (orc_pyramid_roialign_nhwc_f16) is the SAME fp32 arithmetic on fp16 taps with an fp16 result -- not a
+    restatement of anything in the reference, which samples fp32 maps (PyramidROIAlignLayer.swift:186-242).  This test
+    bounds the two roundings it adds against the fp32 layer on the same fp32 maps: on fp16-representable maps only
+    the result rounding remains (half an fp16 ulp: 2^-11 relative), on arbitrary fp32 maps each tap also moves by
+    2^-11 relative, and a bilinear sample is a convex combination of its taps."""
+    import maskrcnn_b200 as m
+    maps = m.synth.feature_maps(3, 256, 256, channels=16)                       # fp32 CHW, N(0, 1)
+    rois = m.synth.random_rois(300, 4, min_px=6, max_px=250, image_size=256, n_pad=5)
+    for pool in (7, 14):
+        want, lv = orc.pyramid_roialign(rois, maps, pool, 256, 256)                                  # the fp32 layer
+        # (1) maps already fp16-representable: only the result is rounded
+        m16 = [x.astype(np.float16) for x in maps]
+        exact_in, _ = orc.pyramid_roialign(rois, [x.astype(np.float32) for x in m16], pool, 256, 256)
+        got, lv2 = orc.pyramid_roialign_nhwc_f16(rois, [np.ascontiguousarray(x.transpose(1, 2, 0)) for x in m16], pool, 256, 256)
+        got = got.astype(np.float32).transpose(0, 3, 1, 2)
+        np.testing.assert_array_equal(lv, lv2)
+        np.testing.assert_array_equal(got, exact_in.astype(np.float16).astype(np.float32))           # = round16(fp32 layer)
+        assert (np.abs(got - exact_in) <= 2.0 ** -11 * np.abs(exact_in) + 2.0 ** -25).all()
+        # (2) arbitrary fp32 maps: taps rounded to fp16 as well; |sample error| <= 2^-11 max|tap| (+ result rounding)
+        bound = 2.0 ** -11 * max(float(np.abs(x).max()) for x in maps) + 2.0 ** -11 * np.abs(want) + 2.0 ** -24
+        assert (np.abs(got - want) <= bound).all()
+        assert np.abs(got - want).max() > 0                                                           # the roundings are real
