@@ -51,11 +51,12 @@ def config_metric(name):
 # --------------------------------------------------------------------------- utils
 def load_traffic(kernel_class):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch for a kernel class, from the committed ncu capture."""
-    p = os.path.join(ROOT, "profiles", "traffic_r1.json")
-    try:
-        return json.load(open(p))[kernel_class]["traffic_bytes_per_launch"]
-    except (OSError, KeyError, ValueError):
-        return None
+    for name in ("traffic_r2.json", "traffic_r1.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name)))[kernel_class]["traffic_bytes_per_launch"]
+        except (OSError, KeyError, ValueError):
+            continue
+    return None
 
 
 def load_peaks():
@@ -459,7 +460,7 @@ class PipelineWorkload:
         peak = peaks["bf16_sustained"]
         return {"kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM convolution, every dense layer)", "bound": "tensor",
                 "achieved": ach, "peak": peak, "peak_source": peaks["source"] + " (sustained cuBLAS bf16; fp16 runs at the same rate)",
-                "unit": "TFLOP/s", "frac": ach / peak, "traffic": load_traffic("conv_gemm_tcgen05"), "traffic_unit": "B/launch (ncu dram bytes, profiles/traffic_r1.json)",
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": load_traffic("conv_gemm_tcgen05"), "traffic_unit": "B/launch (ncu dram bytes, profiles/traffic_r2.json)",
                 "launches": n, "avg_launch_ms": ms / max(n, 1), "algorithmic_flops_per_launch": work / max(n, 1)}
 
     def extra_rooflines(self, prof, peaks):
