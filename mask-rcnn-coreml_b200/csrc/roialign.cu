@@ -307,10 +307,13 @@ __device__ __forceinline__ LanePlan roi_lane_plan(float y1, float x1, float y2, 
 
 // packed version of bilerp2: same operations, same order, each individually rounded (see tl::mul2)
 __device__ __forceinline__ uint32_t bilerp2p(uint32_t a, uint32_t b, uint32_t c, uint32_t d, float lx, float ly, float nz) {
-  const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&a)), fb = __half22float2(*reinterpret_cast<const __half2*>(&b));
-  const float2 fc = __half22float2(*reinterpret_cast<const __half2*>(&c)), fd = __half22float2(*reinterpret_cast<const __half2*>(&d));
-  const float2 top = tl::add2(fa, tl::mul2(tl::sub2(fb, fa), lx, nz));
-  const float2 bot = tl::add2(fc, tl::mul2(tl::sub2(fd, fc), lx, nz));
+  // only the left taps are converted; the right ones enter through the mixed-precision subtraction (r - l in one FHADD)
+  const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&a));
+  const float2 fc = __half22float2(*reinterpret_cast<const __half2*>(&c));
+  const float2 dt = make_float2(tl::sub_h_f((unsigned short)(b & 0xffffu), fa.x), tl::sub_h_f((unsigned short)(b >> 16), fa.y));
+  const float2 db = make_float2(tl::sub_h_f((unsigned short)(d & 0xffffu), fc.x), tl::sub_h_f((unsigned short)(d >> 16), fc.y));
+  const float2 top = tl::add2(fa, tl::mul2(dt, lx, nz));
+  const float2 bot = tl::add2(fc, tl::mul2(db, lx, nz));
   const float2 o = tl::add2(top, tl::mul2(tl::sub2(bot, top), ly, nz));
   const __half2 r = __floats2half2_rn(o.x, o.y);
   return *reinterpret_cast<const uint32_t*>(&r);
@@ -359,8 +362,8 @@ __device__ __forceinline__ HRow hrow(uint32_t row_addr, uint32_t xl_off, uint32_
   #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
-    const float2 fr = __half22float2(*reinterpret_cast<const __half2*>(&rw[i]));
-    h.v[i] = tl::add2(fl, tl::mul2(tl::sub2(fr, fl), lx, nz));
+    const float2 dt = make_float2(tl::sub_h_f((unsigned short)(rw[i] & 0xffffu), fl.x), tl::sub_h_f((unsigned short)(rw[i] >> 16), fl.y));
+    h.v[i] = tl::add2(fl, tl::mul2(dt, lx, nz));
   }
   return h;
 }

@@ -137,6 +137,13 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
       : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return r;
 }
+// d = float(h) - c in one instruction (FHADD; PTX mixed-precision sub, sm_100): the conversion of the fp16 operand is
+// exact, so this is the same single rounding as converting first and subtracting in fp32
+__device__ __forceinline__ float sub_h_f(unsigned short h, float c) {
+  float d;
+  asm("sub.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(h), "f"(c));
+  return d;
+}
 __device__ __forceinline__ float2 mul2(float2 a, float s, float nz) {
   float2 r;
   asm("{.reg .b64 ra, rb, rc, rz; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %4}; mov.b64 rz, {%5, %5};"
