@@ -270,7 +270,9 @@ int mrcnn_pyramid_roialign_eval(mrcnn_ctx* ctx, int batch, const float* rois, in
                                 float* out, int32_t* level_out) {
   if (!ctx) return MRCNN_EINVAL;
   MRCNN_REQUIRE(ctx, rois && fmaps && hw && out, "roialign_eval: null pointer");
-  MRCNN_REQUIRE(ctx, batch >= 1 && R >= 1 && C >= 1 && pool >= 1, "roialign_eval: bad sizes");
+  MRCNN_REQUIRE(ctx, batch >= 1 && R >= 1 && C >= 1 && pool >= 1 && pool <= 64 && roi_row_stride >= 4, "roialign_eval: bad sizes");
+  for (int l = 0; l < 4; ++l)
+    MRCNN_REQUIRE(ctx, fmaps[l] && hw[2 * l] >= 1 && hw[2 * l + 1] >= 1, "roialign_eval: null feature map / bad map size");
   cudaSetDevice(ctx->device);
   Stager st(ctx);
   int rc = MRCNN_OK;
@@ -293,6 +295,10 @@ int mrcnn_roialign_nhwc_f16(mrcnn_ctx* ctx, int batch, const float* rois, int ro
                             void* out, int32_t* level_out) {
   if (!ctx) return MRCNN_EINVAL;
   MRCNN_REQUIRE(ctx, rois && fmaps && hw && out, "roialign_nhwc: null pointer");
+  MRCNN_REQUIRE(ctx, batch >= 1 && R >= 1 && C >= 8 && (C % 8) == 0 && pool >= 1 && pool <= 64 && roi_row_stride >= 4,
+                "roialign_nhwc: bad sizes (channels must be a multiple of 8, 1 <= pool <= 64)");
+  for (int l = 0; l < 4; ++l)      // checked before anything is staged: a NULL level would fault on the device
+    MRCNN_REQUIRE(ctx, fmaps[l] && hw[2 * l] >= 1 && hw[2 * l + 1] >= 1, "roialign_nhwc: null feature map / bad map size");
   cudaSetDevice(ctx->device);
   Stager st(ctx);
   int rc = MRCNN_OK;

@@ -438,3 +438,30 @@ def test_detection_layer_inverted_rois_follow_cgrect_standardisation(pkg, ctx, o
     np.testing.assert_array_equal(det[0], d0)
     b = det[0, :n0, :4]
     assert ((b[:, 2] < b[:, 0]) | (b[:, 3] < b[:, 1])).any()        # inverted boxes are among the detections
+
+
+def test_roialign_abi_rejects_bad_arguments_without_poisoning_the_context(pkg, ctx, orc):
+    """A NULL level pointer, a zero map size or a pool size out of range are refused with MRCNN_EINVAL before anything is
+    staged or launched (a NULL map dereferenced on the device would be a sticky fault); the context keeps working."""
+    import ctypes as C
+    import torch
+    maps = [torch.zeros((1, s, s, 32), dtype=torch.float16, device="cuda") for s in (64, 32, 16, 8)]
+    rois = torch.from_numpy(pkg.synth.random_rois(16, 1)[None]).cuda()
+    out = torch.zeros((1, 16, 7, 7, 32), dtype=torch.float16, device="cuda")
+    hw = (C.c_int32 * 8)(64, 64, 32, 32, 16, 16, 8, 8)
+    lib = pkg.lib()
+    def call(fp, hwv=hw, pool=7, ch=32):
+        return lib.mrcnn_roialign_nhwc_f16(ctx.handle, 1, rois.data_ptr(), 4, 16, fp, hwv, ch, pool, out.data_ptr(), None)
+    good = (C.c_void_p * 4)(*[m.data_ptr() for m in maps])
+    bad = (C.c_void_p * 4)(maps[0].data_ptr(), None, maps[2].data_ptr(), maps[3].data_ptr())
+    assert call(bad) == pkg._cabi.EINVAL and b"null feature map" in lib.mrcnn_last_error(ctx.handle)
+    assert call(good, (C.c_int32 * 8)(64, 64, 0, 32, 16, 16, 8, 8)) == pkg._cabi.EINVAL
+    assert call(good, pool=65) == pkg._cabi.EINVAL and call(good, pool=0) == pkg._cabi.EINVAL
+    assert call(good, ch=36) == pkg._cabi.EINVAL                     # channels must be a multiple of 8
+    fp32 = [torch.zeros((1, 8, s, s), device="cuda") for s in (64, 32, 16, 8)]
+    o32 = torch.zeros((1, 16, 8, 7, 7), device="cuda")
+    badf = (C.c_void_p * 4)(fp32[0].data_ptr(), fp32[1].data_ptr(), None, fp32[3].data_ptr())
+    assert lib.mrcnn_pyramid_roialign_eval(ctx.handle, 1, rois.data_ptr(), 4, 16, badf, hw, 8, 7, o32.data_ptr(), None) == pkg._cabi.EINVAL
+    assert call(good) == 0                                           # the context is still usable
+    ctx.synchronize()
+    assert not out.cpu().numpy().any()                               # zero maps -> zero pooled features

@@ -285,3 +285,38 @@ def test_vertical_tap_groups_same_result_up_to_summation_order(pkg, small, monke
         # propagate through ~50 layers; measured 1.1e-3 (max) / 7e-4 (mean), the size of the fp16-vs-fp32 differences
         assert 0 < mx < 4e-3 and mean < 2e-3, (l, mx, mean)
     assert np.abs(outs[1][1] - outs[0][1]).max() < 2e-3
+
+
+def test_predict_with_a_batch_larger_than_max_batch_after_a_smaller_one(pkg, small):
+    """mrcnn_predict with B > max_batch grows the workspaces on the fly.  Growing a buffer drops the cached graphs
+    (their tensor maps point into it), so every buffer of the call has to be reserved before the graphs are looked
+    up: a first call with 3 images after calls with 2 used to fail with 'mask head not built for this batch'."""
+    cfg = pkg.MaskRCNNConfig()
+    cfg.architecture, cfg.imageShape, cfg.preNMSMaxProposals, cfg.maxProposals, cfg.maxBatch = "resnet50", (SIZE, SIZE, 3), 1000, 200, 1
+    _, blobs = pkg.weights.synthetic_blobs(50)
+    model = pkg.MaskRCNN(cfg, blobs=blobs, anchors=small["anchors"])
+    try:
+        img = small["img"]
+        d1, m1 = model.prediction_batch(img[:1])                   # max_batch
+        big = np.concatenate([img, img[:1]])                       # 3 > max_batch: every per-batch buffer grows
+        d3, m3 = model.prediction_batch(big)
+        np.testing.assert_array_equal(d3[0], d1[0]); np.testing.assert_array_equal(m3[0], m1[0])
+        np.testing.assert_array_equal(d3[2], d1[0]); np.testing.assert_array_equal(m3[2], m1[0])
+        want_d, want_m = small["model"].prediction_batch(img)
+        np.testing.assert_array_equal(d3[:2], want_d); np.testing.assert_array_equal(m3[:2], want_m)
+        d1b, m1b = model.prediction_batch(img[:1])                 # and back to the small batch
+        np.testing.assert_array_equal(d1b, d1); np.testing.assert_array_equal(m1b, m1)
+    finally:
+        model.close()
+
+
+def test_blocking_predict_is_refused_while_streamed_batches_are_in_flight(pkg, small):
+    import torch
+    m, img = small["model"], small["img"]
+    det = torch.zeros((2, 100, 6)).pin_memory(); msk = torch.zeros((2, 100, 28, 28)).pin_memory()
+    m.submit(torch.from_numpy(img).pin_memory(), det, msk)
+    with pytest.raises(pkg.MaskRCNNError, match="in flight"):
+        m.prediction_batch(img)
+    m.wait()
+    want_d, want_m = m.prediction_batch(img)                       # streaming == blocking, bit for bit
+    np.testing.assert_array_equal(det.numpy(), want_d); np.testing.assert_array_equal(msk.numpy(), want_m)
