@@ -653,37 +653,37 @@ roialign_staged_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaArgs
       uint32_t e = d + RA_D_STAB;
       if (NPX == 1) {
         // one sample column per warp: software-pipelined by hand (the waits and shared-memory loads are volatile asm, the
-        // compiler keeps them in order) -- the taps of sample row py + 1 are fetched before the arithmetic of sample row py
-        uint4 e1 = tl::lds128(e + 16);
-        uint2 e2 = tl::lds64(e + 32);
-        uint4 ta, tb, tc, td;
-        {
-          const uint4 e0 = tl::lds128(e);
+        // compiler keeps them in order) -- the taps of sample row py + 1 are fetched before the arithmetic of sample row
+        // py.  Two register sets used alternately (loop unrolled by two): rotating one set costs 20 moves per sample.
+        struct Stage { uint4 ta, tb, tc, td; float ly; uint2 rel; };
+        auto fetch = [&](Stage& st, int py) {
+          const uint32_t ee = e + 48u * (uint32_t)py;
+          const uint4 e0 = tl::lds128(ee), e1 = tl::lds128(ee + 16);
+          st.rel = tl::lds64(ee + 32);
+          st.ly = __uint_as_float(e1.z);
           tl::mbar_wait_nc(e0.z, e1.x);
           tl::mbar_wait_nc(e0.w, e1.y);
-          ta = tl::lds128(e0.x + xe[0].x); tb = tl::lds128(e0.x + xe[0].y);
-          tc = tl::lds128(e0.y + xe[0].x); td = tl::lds128(e0.y + xe[0].y);
-        }
-        #pragma unroll 1
-        for (int py = 0; py < P; ++py, od += P * 32) {
-          uint4 na = ta, nb = tb, nc = tc, nd = td, n1 = e1;
-          uint2 n2 = e2;
-          if (py + 1 < P) {
-            e += 48;
-            const uint4 n0 = tl::lds128(e);
-            n1 = tl::lds128(e + 16); n2 = tl::lds64(e + 32);
-            tl::mbar_wait_nc(n0.z, n1.x);
-            tl::mbar_wait_nc(n0.w, n1.y);
-            na = tl::lds128(n0.x + xe[0].x); nb = tl::lds128(n0.x + xe[0].y);
-            nc = tl::lds128(n0.y + xe[0].x); nd = tl::lds128(n0.y + xe[0].y);
-          }
-          od[0] = bilerp8p(ta, tb, tc, td, __uint_as_float(xe[0].z), __uint_as_float(e1.z), nz);
-          if (e2.x) {                                         // hand back the rows no later sample row reads
+          st.ta = tl::lds128(e0.x + xe[0].x); st.tb = tl::lds128(e0.x + xe[0].y);
+          st.tc = tl::lds128(e0.y + xe[0].x); st.td = tl::lds128(e0.y + xe[0].y);
+        };
+        auto emit = [&](const Stage& st, int py) {
+          od[(size_t)py * P * 32] = bilerp8p(st.ta, st.tb, st.tc, st.td, __uint_as_float(xe[0].z), st.ly, nz);
+          if (st.rel.x) {                                     // hand back the rows no later sample row reads
             __syncwarp();
-            if (lane == 0) { tl::mbar_arrive(e2.x); if (e2.y) tl::mbar_arrive(e2.y); }
+            if (lane == 0) { tl::mbar_arrive(st.rel.x); if (st.rel.y) tl::mbar_arrive(st.rel.y); }
           }
-          ta = na; tb = nb; tc = nc; td = nd; e1 = n1; e2 = n2;
+        };
+        Stage sa, sb;
+        fetch(sa, 0);
+        int py = 0;
+        #pragma unroll 1
+        for (; py + 1 < P; py += 2) {
+          fetch(sb, py + 1);
+          emit(sa, py);
+          if (py + 2 < P) fetch(sa, py + 2);
+          emit(sb, py + 1);
         }
+        if (py < P) emit(sa, py);
       } else {
         #pragma unroll 1
         for (int py = 0; py < P; ++py, e += 48, od += P * 32) {
@@ -858,7 +858,7 @@ struct RoiTmaEntry {                 // tensor maps of one pyramid (they do not 
   const void* p[4]; int hw[8]; int C, batch; bool chw;
   RoiTmaMaps maps; int box_px[4][8]; int cpx;
 };
-struct RoiTmaCache { std::vector<RoiTmaEntry> entries; int ctas = 2; int rowwise = -1; int slot_px = 0; int mode = -1; int ahead = 0; int sorted = -1; };
+struct RoiTmaCache { std::vector<RoiTmaEntry> entries; int ctas = 0; int rowwise = -1; int slot_px = 0; int mode = -1; int ahead = 0; int sorted = -1; };
 
 void roialign_release(mrcnn_ctx* ctx) {
   delete (RoiTmaCache*)ctx->roi_tma;
@@ -874,8 +874,8 @@ static RoiTmaCache* roi_cache(mrcnn_ctx* ctx) {
     const char* es = getenv("MRCNN_ROIALIGN_SLOT_PX");        // widest footprint (pixels) the ring takes: 8, 16, 24 or 32
     cache->slot_px = es ? atoi(es) : 32;
     if (cache->slot_px != 8 && cache->slot_px != 16 && cache->slot_px != 24 && cache->slot_px != 32) cache->slot_px = 32;
-    const char* en = getenv("MRCNN_ROIALIGN_CTAS");           // 3: three CTAs per SM with smaller rings
-    cache->ctas = en ? std::max(2, std::min(4, atoi(en))) : 2;
+    const char* en = getenv("MRCNN_ROIALIGN_CTAS");           // 2 / 3 CTAs per SM (0 = per-kernel default: 3 for pool 7, 2 for pool 14)
+    cache->ctas = en ? std::max(2, std::min(3, atoi(en))) : 0;
     const char* ew = getenv("MRCNN_ROIALIGN_ROWWISE");        // 0 / 1: force the sample-row / feature-row consumer loop
     cache->rowwise = ew ? (atoi(ew) != 0) : -1;
     const char* eo = getenv("MRCNN_ROIALIGN_SORT");           // 0 / 1: process rois in roi order / sorted by (level, y, x)
@@ -990,7 +990,8 @@ static int launch_roialign_tma(mrcnn_ctx* ctx, RoiTmaCache* cache, const RoiTmaM
   const bool roww = cache->rowwise >= 0 ? cache->rowwise != 0 : a.P > 8;
   if (a.P == 7) {
     if (roww) return launch_roialign_tma_t<7, 7, 2, true>(ctx, maps, a);
-    return cache->ctas == 3 ? launch_roialign_tma_t<7, 7, 3, false>(ctx, maps, a) : launch_roialign_tma_t<7, 7, 2, false>(ctx, maps, a);
+      // default three CTAs per SM (21 consumer warps, 70 registers, rings of ~66 KB): equal at batch 8, +8 % at batch 64
+    return cache->ctas == 2 ? launch_roialign_tma_t<7, 7, 2, false>(ctx, maps, a) : launch_roialign_tma_t<7, 7, 3, false>(ctx, maps, a);
   }
   if (a.P == 14) {
     if (!roww) return launch_roialign_tma_t<14, 7, 2, false>(ctx, maps, a);

@@ -50,7 +50,7 @@ def test_reference_arm_prints_the_same_metric_and_config():
 def test_roialign_workload_line_and_reference_arm():
     """configs[4] through bench.py: the committed GPU line carries the three byte models side by side, and the reference arm
     (oracle crop_and_resize on the host cores) prints the same metric."""
-    d = json.load(open(os.path.join(ROOT, "profiles", "r2a_bench_roialign.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2h_bench_roialign.json")))
     assert BASE_KEYS | {"clocks", "gpu_launches", "roofline", "sweep"} <= set(d)
     r = d["roofline"]
     assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
