@@ -1,4 +1,4 @@
-# round 2, call L: full GPU suite + bench lines for configs A / small / single (precise masks default)
+# GPU suite + bench lines for configs A / small / single and the 1-term mask mode
 mkdir -p gpurun_out
 timeout 1800 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2

@@ -1,4 +1,4 @@
-# round 2, call N: warm launch list of one pipeline step (all kernels) + full captures of the latency-bound middle + 2-GPU gather check
+# warm launch list of one pipeline step (all kernels) + full ncu captures of the proposal-stage kernels
 mkdir -p gpurun_out
 # how many launches precede the 4th step: count them from the library (warm-up 3 + 1 launch-count step)
 N=$(python - <<'PY'

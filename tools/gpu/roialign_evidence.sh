@@ -1,4 +1,4 @@
-# ROIAlign evidence: DRAM bytes of every sweep case (ncu metrics pass), the full sweep through bench.py, one full capture each
+# ROIAlign evidence (configs[4]): DRAM bytes of every sweep case (ncu metrics pass), the full sweep through bench.py, one full ncu capture each of the pool-7 and pool-14 kernels
 mkdir -p gpurun_out
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:roialign_staged --csv --log-file gpurun_out/ra_dram.csv \
   python tools/bench_roialign.py --iters 1 --out gpurun_out/ra_dram_sweep.json > gpurun_out/ra_dram.log 2>&1; tail -2 gpurun_out/ra_dram.log

@@ -1,4 +1,4 @@
-# round 2: full GPU suite, smoke, memcheck of the new kernels
+# full GPU suite, smoke, compute-sanitizer memcheck + racecheck of the custom-layer kernels
 mkdir -p gpurun_out
 timeout 1800 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
