@@ -1,24 +1,22 @@
 // roialign.cu -- PyramidROIAlignLayer.evaluate (PyramidROIAlignLayer.swift:79-181).
 //
-//   roi_level_kernel      roisToInputItems (:351-396): FPN level per roi in fp64,
-//                         round half away from zero, clamp 2..5; NaN/inf -> padding
-//   roialign_chw_kernel   boundary layout (reference layout): maps CHW fp32,
-//                         output (R,C,P,P) fp32 (copyOutput :245-274 order)
-//   roialign_nhwc_kernel  internal layout of the fused pipeline: maps NHWC fp16,
-//                         output (R,P,P,C) fp16 (the K-major operand of the head GEMMs)
-// Sampling = MPSNNCropAndResizeBilinear (:212-223) restated as TensorFlow
-// crop_and_resize (bilinear, extrapolation 0) in fp32, every op rounded
-// individually so the result is bit-identical to oracle/oracle.c.
+//   roi_level_kernel        roisToInputItems (:351-396): FPN level per roi in fp64, round half away from zero, clamp
+//                           2..5; NaN / inf -> padding.  Also zeroes the ticket counter of the staged kernel.
+//   roi_order_kernel        processing order of the staged kernel for the boundary layout: per image by (level, y, x)
+//   roialign_staged_kernel  both layouts -- boundary (the reference's): maps CHW fp32, output (R,C,P,P) fp32 (copyOutput
+//                           :245-274 order); internal (fused pipeline): maps NHWC fp16, output (R,P,P,C) fp16 (the
+//                           K-major operand of the head GEMMs).  Persistent, warp-specialised: a planner warp computes
+//                           each roi's tap plan and publishes it as a descriptor in shared memory, an issuer warp
+//                           stages every distinct feature ROW the roi touches through a chunk-allocated mbarrier ring
+//                           (one cp.async.bulk.tensor per row), seven consumer warps compute the P x P samples from
+//                           shared memory with packed fp32 arithmetic; rois are handed out by an atomic ticket.
+//                           Rois the ring cannot serve (inverted boxes, footprints wider than 32 pixels) are gathered
+//                           from global memory inside the same kernel.  DESIGN.md section 4 has the measurements.
+//   roialign_chw_kernel, roialign_nhwc_kernel   pure gather kernels: what TMA boxes cannot cover (more than 256
+//                           channels or not a multiple of 8, pool > 16, unaligned maps) and MRCNN_ROIALIGN=gather.
+// Sampling = MPSNNCropAndResizeBilinear (:212-223) restated as TensorFlow crop_and_resize (bilinear, extrapolation 0) in
+// fp32, every operation rounded individually, so the result is bit-identical to oracle/oracle.c on every path.
 // Every output block is written (fixes Q5: the reference drops the last group).
-//
-//   roialign_staged_kernel   the pipeline's kernel: persistent, warp-specialised.  One producer warp stages the
-//                         feature ROWS a roi touches (every distinct tap row once: box = C channels x 8/16/24 pixels x 1
-//                         row, cp.async.bulk.tensor through an 8-slot mbarrier ring) and seven consumer warps compute
-//                         the P x P samples from shared memory, so a row leaves L2 once per roi instead of once per
-//                         tap, the loads never occupy registers / LSU slots, and the fp32 lerps run as packed
-//                         FADD2 / FFMA2 pairs.  Rois the ring cannot hold (footprint wider than a slot, inverted boxes,
-//                         P > 16) take the gather path inside the same kernel; roialign_nhwc_kernel (pure gather) stays
-//                         for channel counts TMA boxes cannot cover (C > 256).
 #include "common.cuh"
 #include "exact_math.cuh"
 #include "tma_lite.cuh"
@@ -246,7 +244,6 @@ struct RoiTmaArgs {
   int slot_px;                     // widest footprint (pixels) the ring takes (wider rois go the gather way)
   int chunk_bytes;                 // allocation unit of the ring: 8 pixels = 8 * C * 2 bytes (multiple of 128)
   int nch;                         // chunks in the ring
-  int ahead;                       // 1: the planner asks L2 for a roi's rows when it plans it (0: off)
   int* ticket;                     // work counter, zeroed by the level kernel: rois are handed out in order, one at a time
   const int32_t* order;            // processing order (roi_order_kernel) or nullptr = roi order
   int box_px[4][8];                // pixels a box of [level][class] really holds (min(cpx * (class + 1), W of the level))
@@ -449,11 +446,6 @@ roialign_staged_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaArgs
       const uint32_t r0 = (NCH - cursor) / k, per_lap = NCH / k;
       auto row_chunk = [&](uint32_t j) -> uint32_t { return j < r0 ? cursor + j * k : ((j - r0) % per_lap) * k; };
       const int img = item / a.R;
-      if (a.ahead > 0 && ring && lane < 16) {       // optional: ask L2 for the rows now (the issuer is 1-3 rois behind)
-        const CUtensorMap* tm = &maps.m[m][k - 1];
-        if (p.new_lo) tl::tma_prefetch_4d(tm, 0, p.x0, p.lo, img);
-        if (p.new_hi) tl::tma_prefetch_4d(tm, 0, p.x0, p.hi, img);
-      }
       tl::mbar_wait(dempty0 + 8 * (n % RA_DESCS), ((n / RA_DESCS) & 1) ^ 1);     // consumers + issuer are done with this descriptor
       const unsigned yvalid = __ballot_sync(0xffffffffu, lane < 16 && p.ok);
       if (lane == 0) {
@@ -858,7 +850,7 @@ struct RoiTmaEntry {                 // tensor maps of one pyramid (they do not 
   const void* p[4]; int hw[8]; int C, batch; bool chw;
   RoiTmaMaps maps; int box_px[4][8]; int cpx;
 };
-struct RoiTmaCache { std::vector<RoiTmaEntry> entries; int ctas = 0; int rowwise = -1; int slot_px = 0; int mode = -1; int ahead = 0; int sorted = -1; };
+struct RoiTmaCache { std::vector<RoiTmaEntry> entries; int ctas = 0; int rowwise = -1; int slot_px = 0; int mode = -1; int sorted = -1; };
 
 void roialign_release(mrcnn_ctx* ctx) {
   delete (RoiTmaCache*)ctx->roi_tma;
@@ -880,8 +872,6 @@ static RoiTmaCache* roi_cache(mrcnn_ctx* ctx) {
     cache->rowwise = ew ? (atoi(ew) != 0) : -1;
     const char* eo = getenv("MRCNN_ROIALIGN_SORT");           // 0 / 1: process rois in roi order / sorted by (level, y, x)
     cache->sorted = eo ? (atoi(eo) != 0) : -1;
-    const char* ea = getenv("MRCNN_ROIALIGN_AHEAD");          // 1: the planner asks L2 for a roi's rows when it plans it
-    cache->ahead = ea ? std::max(0, std::min(16, atoi(ea))) : 0;
   }
   return cache;
 }
@@ -1027,7 +1017,7 @@ int roialign_nhwc_f16_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int ro
     a.C = (int)C; a.P = P; a.level = lv; a.out = d_out;
     rc = roi_order(ctx, cache, batch, d_rois, roi_stride, R, false, &a.order);
     if (rc) return rc;
-    a.pix = (int)C * 2; a.slot_px = cache->slot_px; a.cpx = e->cpx; a.chunk_bytes = e->cpx * (int)C * 2; a.nch = 0; a.ahead = cache->ahead; a.ticket = ctx->d_roi_level + ctx->roi_cap;
+    a.pix = (int)C * 2; a.slot_px = cache->slot_px; a.cpx = e->cpx; a.chunk_bytes = e->cpx * (int)C * 2; a.nch = 0; a.ticket = ctx->d_roi_level + ctx->roi_cap;
     memcpy(a.box_px, e->box_px, sizeof(a.box_px));
     a.negzero = -0.0f; a.pyr = pyr; memset(&a.pyr32, 0, sizeof(a.pyr32));
     ProfScope ps(ctx, PROF_ROIALIGN, prof_bytes);
@@ -1075,7 +1065,7 @@ int roialign_chw_run(mrcnn_ctx* ctx, int batch, const float* d_rois, int roi_str
     a.C = (int)C; a.P = P; a.level = lv; a.out = d_out;
     rc = roi_order(ctx, cache, batch, d_rois, roi_stride, R, true, &a.order);
     if (rc) return rc;
-    a.pix = 4; a.slot_px = cache->slot_px; a.cpx = e->cpx; a.chunk_bytes = e->cpx * 4 * (int)C; a.nch = 0; a.ahead = 0;
+    a.pix = 4; a.slot_px = cache->slot_px; a.cpx = e->cpx; a.chunk_bytes = e->cpx * 4 * (int)C; a.nch = 0;
     a.ticket = ctx->d_roi_level + ctx->roi_cap;
     memcpy(a.box_px, e->box_px, sizeof(a.box_px));
     a.negzero = -0.0f; a.pyr32 = pyr;

@@ -236,10 +236,10 @@ def test_roialign_nhwc_f16_every_path(pkg, ctx, orc, pool, ch):
 
 
 @pytest.mark.parametrize("env", [{"MRCNN_ROIALIGN": "gather"}, {"MRCNN_ROIALIGN_ROWWISE": "1"}, {"MRCNN_ROIALIGN_ROWWISE": "0"},
-                                 {"MRCNN_ROIALIGN_CTAS": "3"}, {"MRCNN_ROIALIGN_CTAS": "2"}, {"MRCNN_ROIALIGN_SLOT_PX": "8"}, {"MRCNN_ROIALIGN_AHEAD": "1"}])
+                                 {"MRCNN_ROIALIGN_CTAS": "3"}, {"MRCNN_ROIALIGN_CTAS": "2"}, {"MRCNN_ROIALIGN_SLOT_PX": "8"}, {"MRCNN_ROIALIGN_SORT": "1"}])
 def test_roialign_nhwc_f16_kernel_variants_agree(pkg, orc, env, monkeypatch):
     """Every variant of the kernel (pure gather, either consumer loop for either pool size, three CTAs per SM, narrow ring
-    slots = most rois on the gather path, L2 prefetch) gives the oracle's bits.  The knobs are read once per context."""
+    slots = most rois on the gather path, sorted processing order) gives the oracle's bits.  The knobs are read once per context."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     c = pkg.Context()
