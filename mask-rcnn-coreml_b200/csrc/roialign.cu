@@ -421,8 +421,9 @@ roialign_staged_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaArgs
     #pragma unroll 1
     for (;; ++n) {
       // next roi: a ticket (rois in order; CTAs that drew cheap rois simply draw more of them -- no tail of unlucky CTAs)
+      // (the first roi of a CTA is its block index, tickets start after the grid: one atomic round trip less at start-up)
       int item = 0;
-      if (lane == 0) item = atomicAdd(a.ticket, 1);
+      if (lane == 0) item = n == 0 ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(a.ticket, 1);
       if (lane == 0 && item < a.total && a.order) item = __ldg(a.order + item);
       item = __shfl_sync(0xffffffffu, item, 0);
       const uint32_t d = desc0 + (n % RA_DESCS) * RA_D_BYTES;
