@@ -459,7 +459,7 @@ roialign_staged_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaArgs
       if (ring) {
         const int i = lane & 15;
         if (ROWWISE) tl::sts32(d + RA_D_ETAB + 4 * lane, 0u);
-        const int prev_ok = __shfl_up_sync(0xffffffffu, p.ok, 1, 16), next_pos_lo = __shfl_down_sync(0xffffffffu, p.pos_lo, 1, 16);
+        const int next_pos_lo = __shfl_down_sync(0xffffffffu, p.pos_lo, 1, 16);
         __syncwarp();
         if (lane >= 16) {
           if (i < P) sts128(d + RA_D_XTAB + 16 * i, (uint32_t)(p.lo - p.x0) * pix, (uint32_t)(p.hi - p.x0) * pix, __float_as_uint(p.lerp), (uint32_t)p.ok);
@@ -483,7 +483,6 @@ roialign_staged_kernel(const __grid_constant__ RoiTmaMaps maps, const RoiTmaArgs
           if (!ROWWISE && i < P) {
             // sample-row loop: after sample row i the rows before the next sample row's lo tap are done (at most two:
             // older ones went with earlier sample rows); out-of-range sample rows hold pos = rows so far
-            (void)prev_ok;
             const uint32_t qlo = seq + p.pos_lo, qhi = seq + p.pos_hi;
             const int rel0 = i == 0 ? 0 : p.pos_lo, rel1 = i + 1 < P ? next_pos_lo : p.nrows;
             const uint32_t ra = rel1 > rel0 ? empty0 + 8 * ((seq + rel0) % SLOTS) : 0u;
