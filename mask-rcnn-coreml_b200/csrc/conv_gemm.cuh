@@ -61,7 +61,7 @@ struct ConvGemmParams {
   unsigned long long* trace;   // debug: per-CTA event trace (clock64 stamps), nullptr in production (tools/trace_conv.py)
   int ctas;                    // 1 or 2 (CTA pair / cta_group::2), must match the kernel instantiation and the cluster launch
   int nstages;                 // depth of the operand ring (A+B tiles), chosen per layer by the host
-  int nbuf_log2;               // log2 of the number of 16 KB output / residual staging buffers (1 or 2)
+  int nbuf_log2;               // log2 of the number of 16 KB output / residual staging buffers (1, 2 or 3)
   int split_out;               // 1: outputs written as fp16 (hi, lo) pairs: channels [0,cout) = hi, [cout,2cout) = lo (2-term activations)
   int md_precise;              // maskdot: keep the activation in fp32 (no fp16 rounding before the class dot product)
   int maskdot;                 // 1: mask-head tail fused into the deconv epilogue (see epilogue_maskdot)
@@ -191,6 +191,19 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
+// packed fp32 add (FADD2) and the mixed-precision add float(h) + c (FHADD: exact conversion, one rounding)
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc;}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float add_h_f(unsigned short h, float c) {
+  float d;
+  asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(h), "f"(c));
+  return d;
+}
+
 // debug event trace: per CTA three role sections (0 producer, 1 MMA, 2 epilogue) of CG_TRACE_MAX (code << 32 | arg,
 // clock64) pairs, slot 0 of a section = its event count.  Plain stores with a per-thread cursor: nothing on the
 // critical path waits for them.
@@ -298,7 +311,7 @@ template <int BN, int CTAS> struct Cfg {
   static constexpr int kOutStageBytes = CG_BM * 64 * 2;           // one 128-pixel x 64-channel fp16 sub-tile (SWIZZLE_128B)
   static constexpr int kMaxRingPlusOut = (kStagesDeep * kStageBytes + 2 * kOutStageBytes) > (kStagesShort * kStageBytes + 4 * kOutStageBytes)
                                              ? (kStagesDeep * kStageBytes + 2 * kOutStageBytes) : (kStagesShort * kStageBytes + 4 * kOutStageBytes);
-  static constexpr int kBarBytes = 320;                           // mbarriers + TMEM base slot (layout in the kernel)
+  static constexpr int kBarBytes = 416;                           // mbarriers + TMEM base slot (layout in the kernel)
   static constexpr int kSmemBytes = kMaxRingPlusOut + 1024 /*align slack*/ + kBarBytes + BN * 4 /*bias tile*/;
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
 };
@@ -324,12 +337,14 @@ __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, uint8_t
   const int q = warp & 3;
   const int row = q * 32 + lane;
   const int nchunks = (min(BN, p.cout) + 63) / 64;
-  const float lo = p.relu ? 0.0f : -INFINITY;
+  const __half2 lo2 = __float2half2_rn(p.relu ? 0.0f : -INFINITY);
   uint32_t cc = 0;                         // chunk counter of this CTA (staging buffer = cc & nb_mask)
   int bias_n0 = -1;
   int acc = 0; uint32_t acc_phase = 0;
   const uint32_t row_off = (uint32_t)row * 128u;
   const uint32_t sw = (uint32_t)(row & 7);
+  TraceCursor tc = trace_open(p, 2);
+  if (warp != 2 || lane != 0) tc.base = nullptr;                    // one epilogue thread traces (debug only)
   for (int tile = ts.first; tile < ts.total; tile += ts.step) {
     int n0, x0, y0, img;
     ts.coords(p, BN, tile, n0, x0, y0, img);
@@ -348,6 +363,7 @@ __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, uint8_t
       epi_bar_sync();
     }
     mbar_wait(tfull0 + 8u * acc, acc_phase);
+    trace_ev(tc, 5, (uint32_t)tile);       // epilogue: accumulator ready
     tc_fence_after();
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
     #pragma unroll 1
@@ -358,6 +374,7 @@ __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, uint8_t
       const int nc = n0 + c * 64;
       if (RES == 1) mbar_wait(rfull0 + 8u * buf, use & 1u);          // residual chunk has landed (so the buffer is free, too)
       else mbar_wait(sfree0 + 8u * buf, (use & 1u) ^ 1u);            // the store that last used this buffer has read it
+      trace_ev(tc, 9, (uint32_t)c);        // epilogue: staging buffer ready (residual landed / store has read it)
       #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t v[32];
@@ -373,22 +390,28 @@ __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, uint8_t
           if (RES == 2) rq[g] = __ldg(reinterpret_cast<const uint4*>(res_row + nc + hh * 32 + g * 8));
         }
         tmem_ld_wait();
+        // (acc + bias) + residual in fp32, one rounding to fp16, ReLU on the packed halves (max commutes with the
+        // monotonic rounding).  Packed fp32 adds for the bias, the mixed-precision add for the fp16 residual: 92
+        // instead of 160 instructions per 32 columns -- one warp per scheduler runs this, every issue slot is time.
         #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float f[8];
-          #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
-          f[0] += bq[2 * g].x; f[1] += bq[2 * g].y; f[2] += bq[2 * g].z; f[3] += bq[2 * g].w;
-          f[4] += bq[2 * g + 1].x; f[5] += bq[2 * g + 1].y; f[6] += bq[2 * g + 1].z; f[7] += bq[2 * g + 1].w;
+          float2 f[4];
+          f[0] = add2(make_float2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1])), make_float2(bq[2 * g].x, bq[2 * g].y));
+          f[1] = add2(make_float2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])), make_float2(bq[2 * g].z, bq[2 * g].w));
+          f[2] = add2(make_float2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])), make_float2(bq[2 * g + 1].x, bq[2 * g + 1].y));
+          f[3] = add2(make_float2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])), make_float2(bq[2 * g + 1].z, bq[2 * g + 1].w));
           if (RES != 0) {
-            const __half2* rh = reinterpret_cast<const __half2*>(&rq[g]);
+            const uint32_t rw[4] = {rq[g].x, rq[g].y, rq[g].z, rq[g].w};
             #pragma unroll
-            for (int e = 0; e < 4; ++e) { const float2 r2 = __half22float2(rh[e]); f[2 * e] += r2.x; f[2 * e + 1] += r2.y; }
+            for (int e = 0; e < 4; ++e) {
+              f[e].x = add_h_f((unsigned short)(rw[e] & 0xffffu), f[e].x);
+              f[e].y = add_h_f((unsigned short)(rw[e] >> 16), f[e].y);
+            }
           }
           uint4 ov;
           __half2* oh = reinterpret_cast<__half2*>(&ov);
           #pragma unroll
-          for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(fmaxf(f[2 * e], lo), fmaxf(f[2 * e + 1], lo));
+          for (int e = 0; e < 4; ++e) oh[e] = __hmax2(__floats2half2_rn(f[e].x, f[e].y), lo2);
           *reinterpret_cast<uint4*>(srow + ((((uint32_t)(hh * 4 + g)) ^ sw) << 4)) = ov;
         }
       }
@@ -400,6 +423,7 @@ __device__ __forceinline__ void epilogue_staged(const ConvGemmParams& p, uint8_t
       fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the bulk-copy engine
       __syncwarp();
       if (lane == 0) mbar_arrive(sfull0 + 8u * buf);                 // 4 arrivals (one per epilogue warp) = chunk staged
+      trace_ev(tc, 6, (uint32_t)c);        // epilogue: chunk handed to the store thread
     }
     if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
   }
@@ -636,18 +660,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t out_bytes = (uint32_t)C::kOutStageBytes << p.nbuf_log2;
   const uint32_t out_base = smem_base + ring_bytes;                      // nbuf x 16 KB output / residual staging
   const uint32_t bar_base = out_base + out_bytes;
-  // barriers (fixed layout): full[8] @0, empty[8] @64, tmem_full[2] @128, tmem_empty[2] @144, TMEM base slot @160, res_full[4] @168,
-  // patch_full[3] @200, patch_empty[3] @224, store_full[4] @248, store_free[4] @280 (block of Cfg::kBarBytes = 320)
+  // barriers (fixed layout): full[8] @0, empty[8] @64, tmem_full[2] @128, tmem_empty[2] @144, TMEM base slot @160,
+  // patch_full[3] @168, patch_empty[3] @192, res_full[8] @216, store_full[8] @280, store_free[8] @344 (block of Cfg::kBarBytes = 416)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
   auto tfull_bar = [&](int a) { return bar_base + 128u + 8u * a; };
   auto tempty_bar = [&](int a) { return bar_base + 144u + 8u * a; };
   const uint32_t tmem_slot = bar_base + 160u;
-  auto rfull_bar = [&](int b) { return bar_base + 168u + 8u * b; };
-  auto afull_bar = [&](int s) { return bar_base + 200u + 8u * s; };
-  auto aempty_bar = [&](int s) { return bar_base + 224u + 8u * s; };
-  auto sfull_bar = [&](int b) { return bar_base + 248u + 8u * b; };
-  auto sfree_bar = [&](int b) { return bar_base + 280u + 8u * b; };
+  auto afull_bar = [&](int s) { return bar_base + 168u + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar_base + 192u + 8u * s; };
+  auto rfull_bar = [&](int b) { return bar_base + 216u + 8u * b; };
+  auto sfull_bar = [&](int b) { return bar_base + 280u + 8u * b; };
+  auto sfree_bar = [&](int b) { return bar_base + 344u + 8u * b; };
   uint8_t* smem_gen = smem_raw + (smem_base - cg::smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + ring_bytes + out_bytes + 160u);
 
@@ -662,9 +686,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // warps per CTA of the pair (the peer's warps arrive remotely on the leader's barrier)
     for (int s = 0; s < nst; ++s) { cg::mbar_init(full_bar(s), 1); cg::mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { cg::mbar_init(tfull_bar(a), 1); cg::mbar_init(tempty_bar(a), 4 * CTAS); }
-    for (int b = 0; b < 4; ++b) cg::mbar_init(rfull_bar(b), 1);
+    for (int b = 0; b < 8; ++b) cg::mbar_init(rfull_bar(b), 1);
     for (int a = 0; a < 3; ++a) { cg::mbar_init(afull_bar(a), 1); cg::mbar_init(aempty_bar(a), 1); }
-    for (int b = 0; b < 4; ++b) { cg::mbar_init(sfull_bar(b), 4); cg::mbar_init(sfree_bar(b), 1); }
+    for (int b = 0; b < 8; ++b) { cg::mbar_init(sfull_bar(b), 4); cg::mbar_init(sfree_bar(b), 1); }
     cg::fence_barrier_init();
   }
   if (warp == 1) { if (CTAS == 2) cg::tmem_alloc_2cta(tmem_slot, C::kTmemCols); else cg::tmem_alloc(tmem_slot, C::kTmemCols); }

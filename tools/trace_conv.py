@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-CTA role timeline of one convolution launch (debug): producer / MMA / epilogue events with clock64 stamps.
-usage: python tools/trace_conv.py n h w cin cout k stride [ctas]"""
+usage: python tools/trace_conv.py n h w cin cout k stride [ctas] [residual: 0|1]"""
 import os
 import sys
 
@@ -10,13 +10,14 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import maskrcnn_b200 as m
 
-NAMES = {0: "prologue_done", 7: "dep_ok", 1: "P.issue", 2: "M.landed", 3: "M.tile_start", 4: "M.tile_issued", 5: "E.acc_ready", 6: "E.chunk_stored", 8: "E.done"}
+NAMES = {0: "prologue_done", 7: "dep_ok", 1: "P.issue", 2: "M.landed", 3: "M.tile_start", 4: "M.tile_issued", 5: "E.acc_ready", 9: "E.buf_ready", 6: "E.chunk_staged", 8: "E.done"}
 
 
 def main():
     n, h, w, cin, cout, k, stride = [int(x) for x in sys.argv[1:8]]
     if len(sys.argv) > 8:
-        os.environ["MRCNN_CONV_CTAS"] = sys.argv[8]
+        if int(sys.argv[8]):
+            os.environ["MRCNN_CONV_CTAS"] = sys.argv[8]
     ctx = m.Context()
     st = torch.cuda.Stream()
     ctx.set_stream(st.cuda_stream)
@@ -28,6 +29,9 @@ def main():
     bias = torch.zeros(cout, device="cuda")
     out = torch.empty((n, ho, wo, (cout + 7) // 8 * 8), device="cuda", dtype=torch.float16)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    res = None
+    if len(sys.argv) > 9 and int(sys.argv[9]):
+        res = torch.randn((n, ho, wo, cout), device="cuda", dtype=torch.float16)
     SEC = 2 * 340 + 2
     trace = torch.zeros(148 * 3 * SEC, dtype=torch.int64, device="cuda")
     with torch.cuda.stream(st):
@@ -36,7 +40,7 @@ def main():
             trace.zero_()
             st.synchronize()
             lib.mrcnn_debug_conv_trace(trace.data_ptr() if it == 2 else None)
-            rc = lib.mrcnn_conv2d_nhwc_f16(ctx.handle, x.data_ptr(), n, h, w, cin, wt.data_ptr(), bias.data_ptr(), cout, k, k, stride, pad, None, 1, out.data_ptr())
+            rc = lib.mrcnn_conv2d_nhwc_f16(ctx.handle, x.data_ptr(), n, h, w, cin, wt.data_ptr(), bias.data_ptr(), cout, k, k, stride, pad, res.data_ptr() if res is not None else None, 1, out.data_ptr())
             m._cabi.check(ctx.handle, rc)
             st.synchronize()
     lib.mrcnn_debug_conv_trace(None)
