@@ -4,7 +4,7 @@ tensor-pipe activity per launch) with the layer plan of the dense graphs (execut
 per layer class: launches, time, share of the step, achieved TFLOP/s, tensor-pipe activity, tiles per launch and the
 wave count on 148 SMs, and the time the class would take at the measured sustained peak (MEASURED_PEAKS.json) -- i.e.
 where the step's time goes and how much of it is above the roofline.  Pure post-processing: no GPU needed.
-  python tools/layer_breakdown.py profiles/r1w_pipeline_launches_warm.csv > profiles/r1w_conv_layer_breakdown.txt"""
+  python tools/layer_breakdown.py profiles/r1w_pipeline_launches_warm.csv [--traffic-json profiles/traffic_r2.json] > profiles/r1w_conv_layer_breakdown.txt"""
 import collections
 import csv
 import io
@@ -141,6 +141,28 @@ def main():
     print("\n# other kernels (ms per step)")
     for k, v in other.most_common():
         print(f"{k:34s} {v / 1e6:7.3f} {100 * v / step_ns:5.1f}%")
+    if "--traffic-json" in sys.argv:
+        # per-class DRAM traffic of the step (bench.py reads roofline.traffic from this file)
+        out = sys.argv[sys.argv.index("--traffic-json") + 1]
+        rd = sum(d["dram__bytes_read.sum"] for d in convs)
+        wr = sum(d["dram__bytes_write.sum"] for d in convs)
+        ra = [d for d in launches if "roialign_staged_kernel" in d["name"] or "roialign_nhwc_kernel" in d["name"]]
+        json.dump({
+            "source": f"profiles/{os.path.basename(path)} ({len(launches)} launches = one warm batch-{B} step): ncu --metrics gpu__time_duration.sum,"
+                      "dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active... --clock-control none --cache-control none "
+                      "(python bench.py --steps 1 --warmup 3); written by tools/layer_breakdown.py --traffic-json",
+            "conv_gemm_tcgen05": {
+                "launches_per_step": len(convs), "dram_bytes_read_per_step": int(rd), "dram_bytes_write_per_step": int(wr),
+                "traffic_bytes_per_launch": int((rd + wr) / len(convs)),
+                "note": "average over the conv launches of a step (layer sizes differ by 3 orders of magnitude)",
+                "share_of_step_time_ncu": round(conv_ns / step_ns, 3),
+                "tensor_pipe_active_time_weighted_pct": round(sum(a["tens"] for a in agg.values()) / conv_ns, 1)},
+            "roialign": {
+                "launches_per_step": len(ra),
+                "traffic_bytes_per_launch": int(sum(d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"] for d in ra) / max(len(ra), 1)),
+                "per_launch": [{"kernel": d["name"].split("(")[0], "dram_read": d["dram__bytes_read.sum"], "dram_write": d["dram__bytes_write.sum"],
+                                "us_under_ncu": d["gpu__time_duration.sum"] / 1e3} for d in ra]},
+        }, open(out, "w"), indent=1)
 
 
 if __name__ == "__main__":
