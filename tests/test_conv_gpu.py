@@ -63,3 +63,76 @@ def test_conv_matches_torch(pkg, ctx, case):
     err = (got - ref).abs().max().item()
     scale = ref.abs().max().item()
     assert err <= 2e-3 * max(scale, 1.0), f"max abs err {err} (scale {scale})"
+
+
+@pytest.mark.parametrize("relu", [True, False])
+def test_conv_epilogue_rounds_once(pkg, ctx, relu):
+    """The epilogue contract: out = fp16(relu(acc + bias + residual)) with ONE rounding (fp32 sum, packed / mixed-precision
+    adds in the kernel).  Against an fp64 evaluation rounded once to fp16: at most one fp16 ulp away (the fp32 accumulation
+    order differs), almost always equal; clamped outputs are +0, never -0."""
+    import torch
+    n, h, w, cin, cout = 4, 32, 32, 128, 256
+    g = torch.Generator(device="cpu").manual_seed(1234 + relu)
+    x = torch.randn(n, h, w, cin, generator=g).half().cuda()
+    wt = (torch.randn(cout, 1, 1, cin, generator=g) / np.sqrt(cin)).half().cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    res = torch.randn(n, h, w, cout, generator=g).half().cuda()
+    out = torch.full((n, h, w, cout), 77.0, dtype=torch.float16, device="cuda")
+    rc = pkg.lib().mrcnn_conv2d_nhwc_f16(ctx.handle, x.data_ptr(), n, h, w, cin, wt.data_ptr(), bias.data_ptr(), cout, 1, 1,
+                                         1, 0, res.data_ptr(), int(relu), out.data_ptr())
+    pkg._cabi.check(ctx.handle, rc)
+    ctx.synchronize()
+    ref = x.double().reshape(-1, cin) @ wt.double().reshape(cout, cin).t() + bias.double() + res.double().reshape(-1, cout)
+    if relu:
+        ref = torch.relu(ref)
+    want = ref.half().reshape(n, h, w, cout)
+    gb = out.view(torch.int16).int()
+    wb = want.view(torch.int16).int()
+    # fp16 bit patterns of equal sign are ordered like the values: a difference of 1 in the pattern is one ulp
+    same_sign = (gb < 0) == (wb < 0)
+    ulp = (gb - wb).abs()
+    near_zero = (out.float().abs() < 1e-3) & (want.float().abs() < 1e-3)       # sign may flip across zero
+    assert bool(((ulp <= 1) & same_sign | near_zero).all()), f"max ulp distance {int(ulp[same_sign].max())}"
+    assert float((gb == wb).float().mean()) > 0.995
+    if relu:
+        assert int((gb < 0).sum()) == 0, "ReLU outputs must not carry a sign bit (-0)"
+        assert bool((out[ref.reshape(n, h, w, cout) <= 0] == 0).all())
+
+
+def test_conv_grid_variants_bit_identical(tmp_path):
+    """MRCNN_CONV_BALANCED (balanced persistent grid vs one CTA per SM) and MRCNN_CONV_CTAS (CTA pairs vs single CTAs) change
+    the schedule, never the result (same K order per output row): the knobs are read once per process, so each variant runs
+    in its own interpreter.  (MRCNN_CONV_VGROUP reorders the taps, i.e. the fp32 summation: equal only within tolerance.)"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = r'''
+import sys, zlib
+sys.path.insert(0, %r)
+import numpy as np, torch
+import maskrcnn_b200 as m
+ctx = m.Context()
+crc = 0
+for (n, h, w, cin, cout, k, res) in [(8, 64, 64, 256, 1024, 1, True), (8, 64, 64, 256, 256, 3, False), (3, 50, 38, 64, 128, 3, True)]:
+    g = torch.Generator(device="cpu").manual_seed(7)
+    x = torch.randn(n, h, w, cin, generator=g).half().cuda()
+    wt = (torch.randn(cout, k, k, cin, generator=g) / np.sqrt(k * k * cin)).half().cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    r = torch.randn(n, h, w, cout, generator=g).half().cuda() if res else None
+    out = torch.zeros((n, h, w, cout), dtype=torch.float16, device="cuda")
+    rc = m.lib().mrcnn_conv2d_nhwc_f16(ctx.handle, x.data_ptr(), n, h, w, cin, wt.data_ptr(), bias.data_ptr(), cout, k, k, 1, k // 2,
+                                       r.data_ptr() if res else None, 1, out.data_ptr())
+    m._cabi.check(ctx.handle, rc)
+    ctx.synchronize()
+    crc = zlib.crc32(out.cpu().numpy().tobytes(), crc)
+print("CRC", crc)
+''' % root
+    crcs = {}
+    for name, env in [("default", {}), ("one CTA per SM", {"MRCNN_CONV_BALANCED": "0"}), ("single CTAs", {"MRCNN_CONV_CTAS": "1"})]:
+        e = dict(os.environ)
+        e.update(env)
+        p = subprocess.run([sys.executable, "-c", script], env=e, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        crcs[name] = [ln for ln in p.stdout.splitlines() if ln.startswith("CRC")][-1]
+    assert len(set(crcs.values())) == 1, crcs
