@@ -316,6 +316,13 @@ MRCNN_API int mrcnn_conv2d_nhwc_f16(mrcnn_ctx* ctx, const void* x, int n, int h,
                           int cin, const void* wgt, const float* bias, int cout,
                           int kh, int kw, int stride, int pad,
                           const void* residual, int relu, void* out);
+/* Test hook: a bottleneck block's 1x1 expansion with residual and the next block's 1x1 reduction in ONE launch
+ * (csrc/conv_fused.cuh): X = relu(a * w1^T + b1 + residual) [n,h,w,n1], Y = relu(X * w2^T + b2) [n,h,w,n2];
+ * a [n,h,w,c1] f16 (c1 <= 256, % 64), w1 [n1,c1] f16 (n1 % 256 == 0), w2 [n2,n1] f16 (n2 = 64 / 128 / 256).
+ * Bit-identical to two mrcnn_conv2d_nhwc_f16 calls.  Device pointers only. */
+MRCNN_API int mrcnn_debug_fused_expand_reduce(mrcnn_ctx* ctx, const void* a, int n, int h, int w, int c1,
+                          const void* w1, const float* b1, int n1, const void* residual,
+                          const void* w2, const float* b2, int n2, void* x_out, void* y_out);
 /* Debug: per-CTA event trace (clock64 stamps of the producer / MMA / epilogue roles) of the next
  * mrcnn_conv2d_nhwc_f16 calls; device buffer of 148 * 3 * (2*340 + 2) u64, NULL = off (tools/trace_conv.py). */
 MRCNN_API int mrcnn_debug_conv_trace(void* device_buffer);

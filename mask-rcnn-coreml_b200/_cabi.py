@@ -84,6 +84,7 @@ SIGNATURES = {
     "mrcnn_roialign_nhwc_f16": (_i, [_vp, _i, _vp, _i, _i64, C.POINTER(_vp), C.POINTER(C.c_int32), _i64, _i, _vp, _vp]),
     "mrcnn_conv2d_nhwc_f16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "mrcnn_debug_conv_trace": (_i, [_vp]),
+    "mrcnn_debug_fused_expand_reduce": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "mrcnn_backbone_eval": (_i, [_vp, _i, _vp, C.POINTER(_vp), _vp, _vp]),
 }
 

@@ -1,6 +1,7 @@
 // dense.cu -- host side of the tcgen05 implicit-GEMM convolution (conv_gemm.cuh):
 // TMA tensor-map construction, tile-shape selection and launch.
 #include "dense.h"
+#include "conv_fused.cuh"
 #include <string.h>
 #include <stdlib.h>
 #include <algorithm>
@@ -268,6 +269,91 @@ int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan) {
   return MRCNN_OK;
 }
 
+// ---- fused expansion + reduction (conv_fused.cuh) ---------------------------------------------------------------
+bool fused_plan_supported(const ConvLaunch& e, const ConvLaunch& r) {
+  const int ho = e.h_out ? e.h_out : e.h_in, wo = e.w_out ? e.w_out : e.w_in;
+  return e.kh == 1 && e.kw == 1 && e.stride == 1 && e.pad == 0 && !e.ntaps_override && !e.custom_view && !e.deconv && !e.maskdot &&
+         !e.split_out && !e.out_f32 && e.residual && e.res_mode == 1 && e.bias && e.out &&
+         e.cin % 64 == 0 && e.cin <= 256 && (e.ld_in == 0 || e.ld_in == e.cin) && e.cout % 256 == 0 && (e.ldc == 0 || e.ldc == e.cout) &&
+         (e.res_ld == 0 || e.res_ld == e.cout) && (e.res_h == 0 || e.res_h == ho) && (e.res_w == 0 || e.res_w == wo) &&
+         r.kh == 1 && r.kw == 1 && r.stride == 1 && r.pad == 0 && !r.ntaps_override && !r.custom_view && !r.deconv && !r.maskdot &&
+         !r.split_out && !r.out_f32 && !r.residual && r.bias && r.out &&
+         (const void*)r.x == (const void*)e.out && r.cin == e.cout && (r.ld_in == 0 || r.ld_in == r.cin) &&
+         (r.cout == 64 || r.cout == 128 || r.cout == 256) && (r.ldc == 0 || r.ldc == r.cout) &&
+         r.n == e.n && r.h_in == ho && r.w_in == wo;
+}
+
+static int encode_act_map(mrcnn_ctx* ctx, PFN_tmapEncodeTiled enc, CUtensorMap* map, const void* base, int channels, int n, int h, int w,
+                          int tw, int th, const char* what) {
+  cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t str[3] = {(cuuint64_t)channels * 2, (cuuint64_t)channels * 2 * w, (cuuint64_t)channels * 2 * w * h};
+  cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return mrcnn_fail(ctx, MRCNN_ECUDA, std::string("fused conv: cuTensorMapEncodeTiled(") + what + ") failed");
+  return MRCNN_OK;
+}
+
+static int encode_weight_map(mrcnn_ctx* ctx, PFN_tmapEncodeTiled enc, CUtensorMap* map, const void* base, int k, int rows, int box_rows,
+                             const char* what) {
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t str[1] = {(cuuint64_t)k * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return mrcnn_fail(ctx, MRCNN_ECUDA, std::string("fused conv: cuTensorMapEncodeTiled(") + what + ") failed");
+  return MRCNN_OK;
+}
+
+int fused_plan_build(mrcnn_ctx* ctx, const ConvLaunch& e, const ConvLaunch& r, FusedPlan* plan) {
+  PFN_tmapEncodeTiled enc = get_encode_fn();
+  if (!enc) return mrcnn_fail(ctx, MRCNN_ECUDA, "conv: cuTensorMapEncodeTiled not available from the driver");
+  MRCNN_REQUIRE(ctx, fused_plan_supported(e, r), "fused conv: the two layers are not a 1x1 expansion with residual followed by a 1x1 reduction");
+  FusedParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  p.n_img = e.n; p.h = e.h_in; p.w = e.w_in;
+  if (p.w > 8) { p.tw = 16; p.th = 8; } else { p.tw = 8; p.th = 16; }
+  p.tiles_x = ceil_div(p.w, p.tw); p.tiles_y = ceil_div(p.h, p.th);
+  p.c1 = e.cin; p.n1 = e.cout; p.n2 = r.cout;
+  p.relu1 = e.relu; p.relu2 = r.relu;
+  p.bias1 = e.bias; p.bias2 = r.bias;
+  int rc;
+  if ((rc = encode_act_map(ctx, enc, &plan->tmA, e.x, p.c1, p.n_img, p.h, p.w, p.tw, p.th, "A"))) return rc;
+  if ((rc = encode_act_map(ctx, enc, &plan->tmR, e.residual, p.n1, p.n_img, p.h, p.w, p.tw, p.th, "R"))) return rc;
+  if ((rc = encode_act_map(ctx, enc, &plan->tmX, e.out, p.n1, p.n_img, p.h, p.w, p.tw, p.th, "X"))) return rc;
+  if ((rc = encode_act_map(ctx, enc, &plan->tmY, r.out, p.n2, p.n_img, p.h, p.w, p.tw, p.th, "Y"))) return rc;
+  if ((rc = encode_weight_map(ctx, enc, &plan->tmB1, e.w, p.c1, p.n1, 128, "W1"))) return rc;
+  if ((rc = encode_weight_map(ctx, enc, &plan->tmB2, r.w, p.n1, p.n2, p.n2, "W2"))) return rc;
+  const long tiles = (long)p.n_img * p.tiles_x * p.tiles_y, slots = ctx->sm_count;
+  const long rounds = (tiles + slots - 1) / slots;
+  plan->grid = (int)((tiles + rounds - 1) / rounds);              // balanced grid (see conv_plan_build)
+  const double px = (double)p.n_img * p.h * p.w;
+  plan->flops = 2.0 * px * ((double)p.n1 * p.c1 + (double)p.n2 * p.n1);
+  return MRCNN_OK;
+}
+
+int fused_plan_run(mrcnn_ctx* ctx, const FusedPlan& plan) {
+  static bool attr_done[64] = {false};
+  const int dv = ctx->device & 63;
+  if (!attr_done[dv]) {
+    MRCNN_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_fused_expand_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cgf::kSmemBytes));
+    attr_done[dv] = true;
+  }
+  ProfScope ps(ctx, PROF_CONV_GEMM, plan.flops);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(plan.grid); cfg.blockDim = dim3(CG_THREADS);
+  cfg.dynamicSmemBytes = cgf::kSmemBytes; cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  MRCNN_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, conv_fused_expand_reduce_kernel, plan.tmA, plan.tmB1, plan.tmB2, plan.tmR, plan.tmX, plan.tmY, plan.p));
+  MRCNN_LAUNCH_CHECK(ctx);
+  return MRCNN_OK;
+}
+
 static unsigned long long* g_trace_buf = nullptr;   // set by mrcnn_debug_conv_trace; picked up by the conv2d hook only
 
 extern "C" {
@@ -295,6 +381,22 @@ MRCNN_API int mrcnn_conv2d_nhwc_f16(mrcnn_ctx* ctx, const void* x, int n, int h,
   int rc = conv_plan_build(ctx, L, &plan);
   if (rc) return rc;
   return conv_plan_run(ctx, plan);
+}
+
+// Test hook: X = relu(a * w1^T + b1 + residual) [n,h,w,n1] and Y = relu(X * w2^T + b2) [n,h,w,n2] in one launch
+// (conv_fused.cuh); a [n,h,w,c1] f16, w1 [n1,c1] f16, w2 [n2,n1] f16, biases f32.  Device pointers only.
+MRCNN_API int mrcnn_debug_fused_expand_reduce(mrcnn_ctx* ctx, const void* a, int n, int h, int w, int c1, const void* w1, const float* b1,
+                                              int n1, const void* residual, const void* w2, const float* b2, int n2, void* x_out, void* y_out) {
+  if (!ctx) return MRCNN_EINVAL;
+  cudaSetDevice(ctx->device);
+  ConvLaunch e, r;
+  e.x = (const __half*)a; e.n = n; e.h_in = h; e.w_in = w; e.cin = c1; e.w = (const __half*)w1; e.cout = n1; e.bias = b1;
+  e.residual = (const __half*)residual; e.res_mode = 1; e.relu = 1; e.out = x_out;
+  r.x = (const __half*)x_out; r.n = n; r.h_in = h; r.w_in = w; r.cin = n1; r.w = (const __half*)w2; r.cout = n2; r.bias = b2; r.relu = 1; r.out = y_out;
+  FusedPlan plan;
+  int rc = fused_plan_build(ctx, e, r, &plan);
+  if (rc) return rc;
+  return fused_plan_run(ctx, plan);
 }
 
 }  // extern "C"

@@ -54,6 +54,25 @@ struct ConvPlan {
 int conv_plan_build(mrcnn_ctx* ctx, const ConvLaunch& L, ConvPlan* plan);
 int conv_plan_run(mrcnn_ctx* ctx, const ConvPlan& plan);
 
+// A bottleneck block's 1x1 expansion (+ residual) and the next block's 1x1 reduction as one launch (conv_fused.cuh)
+struct FusedParams {
+  int n_img, h, w;             // pixels (both layers: 1x1, stride 1)
+  int tw, th, tiles_x, tiles_y;
+  int c1, n1, n2;              // channels: A, X, Y
+  int relu1, relu2;
+  const float* bias1;          // [n1]
+  const float* bias2;          // [n2]
+};
+struct FusedPlan {
+  CUtensorMap tmA, tmB1, tmB2, tmR, tmX, tmY;
+  FusedParams p;
+  int grid = 0;
+  double flops = 0;
+};
+bool fused_plan_supported(const ConvLaunch& expand, const ConvLaunch& reduce);
+int fused_plan_build(mrcnn_ctx* ctx, const ConvLaunch& expand, const ConvLaunch& reduce, FusedPlan* plan);
+int fused_plan_run(mrcnn_ctx* ctx, const FusedPlan& plan);
+
 int dense_load_weights(mrcnn_ctx* ctx, int which, const void* blob, size_t bytes);
 void dense_destroy(mrcnn_ctx* ctx);
 void comm_destroy(mrcnn_ctx* ctx);

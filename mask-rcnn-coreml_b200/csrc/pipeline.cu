@@ -196,9 +196,21 @@ static int add_conv(mrcnn_ctx* ctx, Graph& g, int which, const ConvArgs& a) {
 
 // A ResNet stage: its layers, launched one by one.  (Two experiments that regrouped these launches lost on B200 and were
 // removed: one persistent dataflow launch per stage, and per-sub-batch launches to keep a block in L2 -- DESIGN.md 8.)
+// A block's 1x1 expansion (+ residual) followed by the next block's 1x1 reduction is ONE launch where the fused kernel
+// supports the shapes (csrc/conv_fused.cuh; MRCNN_CONV_FUSE=0 launches them separately, results are bit-identical).
 static int add_stage(mrcnn_ctx* ctx, Graph& g, const std::vector<ConvLaunch>& layers) {
-  for (const ConvLaunch& L : layers) {
-    int rc = add_conv_launch(ctx, g, L, "resnet stage layer");
+  static int env_fuse = -1;
+  if (env_fuse < 0) { const char* e = getenv("MRCNN_CONV_FUSE"); env_fuse = e ? atoi(e) : 1; }
+  for (size_t i = 0; i < layers.size(); ++i) {
+    if (env_fuse && i + 1 < layers.size() && fused_plan_supported(layers[i], layers[i + 1])) {
+      auto plan = std::make_shared<FusedPlan>();
+      int rc = fused_plan_build(ctx, layers[i], layers[i + 1], plan.get());
+      if (rc) { ctx->err = "resnet stage, fused expansion + reduction: " + ctx->err; return rc; }
+      g.push_back([plan](mrcnn_ctx* c) { return fused_plan_run(c, *plan); });
+      ++i;
+      continue;
+    }
+    int rc = add_conv_launch(ctx, g, layers[i], "resnet stage layer");
     if (rc) return rc;
   }
   return MRCNN_OK;

@@ -136,3 +136,46 @@ print("CRC", crc)
         assert p.returncode == 0, p.stderr[-2000:]
         crcs[name] = [ln for ln in p.stdout.splitlines() if ln.startswith("CRC")][-1]
     assert len(set(crcs.values())) == 1, crcs
+
+
+FUSED_CASES = [
+    # n, h, w, c1, n1, n2
+    (8, 64, 64, 256, 1024, 256),       # res4 at batch 8: 256 tiles, two per CTA
+    (2, 30, 38, 128, 512, 128),        # res3-like, ragged tiles
+    (1, 16, 16, 64, 256, 64),          # res2-like, two chunks per tile, a single Y sub-chunk
+    (3, 64, 64, 256, 1024, 256),
+    (4, 64, 128, 64, 256, 64),         # several tiles per CTA with one Y sub-chunk (the store thread frees it at the tile's end)
+    (8, 64, 96, 128, 512, 128),        # several tiles per CTA, two Y sub-chunks
+    (8, 128, 128, 256, 1024, 256),     # seven tiles per CTA
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES)
+def test_fused_expand_reduce_bit_identical(pkg, ctx, case):
+    """csrc/conv_fused.cuh: the 1x1 expansion (+ residual) of a bottleneck block and the 1x1 reduction of the next block in
+    one launch == the two separate launches, bit for bit (X and Y)."""
+    import torch
+    n, h, w, c1, n1, n2 = case
+    g = torch.Generator(device="cpu").manual_seed(hash(case) & 0xffff)
+    a = torch.randn(n, h, w, c1, generator=g).half().cuda()
+    w1 = (torch.randn(n1, 1, 1, c1, generator=g) / np.sqrt(c1)).half().cuda()
+    b1 = torch.randn(n1, generator=g).cuda()
+    res = torch.randn(n, h, w, n1, generator=g).half().cuda()
+    w2 = (torch.randn(n2, 1, 1, n1, generator=g) / np.sqrt(n1)).half().cuda()
+    b2 = torch.randn(n2, generator=g).cuda()
+    lib = pkg.lib()
+    x_ref = torch.full((n, h, w, n1), 7.0, dtype=torch.float16, device="cuda")
+    y_ref = torch.full((n, h, w, n2), 7.0, dtype=torch.float16, device="cuda")
+    torch.cuda.synchronize()
+    pkg._cabi.check(ctx.handle, lib.mrcnn_conv2d_nhwc_f16(ctx.handle, a.data_ptr(), n, h, w, c1, w1.data_ptr(), b1.data_ptr(), n1, 1, 1, 1, 0,
+                                                          res.data_ptr(), 1, x_ref.data_ptr()))
+    pkg._cabi.check(ctx.handle, lib.mrcnn_conv2d_nhwc_f16(ctx.handle, x_ref.data_ptr(), n, h, w, n1, w2.data_ptr(), b2.data_ptr(), n2, 1, 1, 1, 0,
+                                                          None, 1, y_ref.data_ptr()))
+    x = torch.full((n, h, w, n1), 9.0, dtype=torch.float16, device="cuda")
+    y = torch.full((n, h, w, n2), 9.0, dtype=torch.float16, device="cuda")
+    torch.cuda.synchronize()           # the context's stream is non-blocking: the fills above must not race the kernel
+    pkg._cabi.check(ctx.handle, lib.mrcnn_debug_fused_expand_reduce(ctx.handle, a.data_ptr(), n, h, w, c1, w1.data_ptr(), b1.data_ptr(), n1,
+                                                                    res.data_ptr(), w2.data_ptr(), b2.data_ptr(), n2, x.data_ptr(), y.data_ptr()))
+    ctx.synchronize()
+    assert torch.equal(x, x_ref), f"X differs in {(x != x_ref).sum().item()} of {x.numel()} elements"
+    assert torch.equal(y, y_ref), f"Y differs in {(y != y_ref).sum().item()} of {y.numel()} elements"
