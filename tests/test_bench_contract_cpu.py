@@ -11,7 +11,7 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def test_committed_gpu_line_has_the_contract_keys():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r2j_pipeline_bench_A.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2k_pipeline_bench_A.json")))
     assert BASE_KEYS | {"clocks", "gpu_launches", "roofline"} <= set(d)
     assert d["metric"].startswith("images/sec") and d["unit"] == "images/s" and d["higher_is_better"] is True
     assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
@@ -38,7 +38,7 @@ def test_reference_arm_prints_the_same_metric_and_config():
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1                                                  # ONE JSON line on stdout
     d = json.loads(lines[0])
-    gpu = json.load(open(os.path.join(ROOT, "profiles", "r2j_pipeline_bench_A.json")))
+    gpu = json.load(open(os.path.join(ROOT, "profiles", "r2k_pipeline_bench_A.json")))
     assert d["impl"] == "reference" and BASE_KEYS <= set(d)
     assert (d["metric"], d["unit"], d["higher_is_better"]) == (gpu["metric"], gpu["unit"], gpu["higher_is_better"])
     for k in ("workload", "name", "image", "batch_per_gpu", "pre_nms", "rois", "detections", "model"):

@@ -10,7 +10,7 @@ def test_layer_breakdown_on_the_committed_launch_list():
     """tools/layer_breakdown.py: the 130 conv launches of the ncu list line up with the layer plan (it asserts the
     count), and the totals agree with what bench.py measured live for the same tree (conv class 0.59 of the tensor peak)."""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "layer_breakdown.py"),
-                        os.path.join(ROOT, "profiles", "r1w_pipeline_launches_warm.csv"), "--one-term-masks"], capture_output=True, text=True, timeout=120)
+                        os.path.join(ROOT, "profiles", "r1w_pipeline_launches_warm.csv"), "--one-term-masks", "--unfused"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
     total = [l for l in r.stdout.splitlines() if l.startswith("all conv launches")]
     assert len(total) == 1

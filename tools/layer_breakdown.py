@@ -19,6 +19,7 @@ B, IMG, R, D = 8, 1024, 1000, 100
 
 
 ONE_TERM_MASKS = "--one-term-masks" in sys.argv      # launch lists taken with precise_masks = 0 (round 1)
+UNFUSED = "--unfused" in sys.argv                    # launch lists taken before csrc/conv_fused.cuh (or with MRCNN_CONV_FUSE=0)
 
 
 def plan(architecture=101):
@@ -27,22 +28,29 @@ def plan(architecture=101):
     L = []
 
     def add(cls, M, N, K, cin, extra=0, out_bytes=None):
-        L.append((cls, M, N, K, 2 * M * cin + 2 * N * K + (2 * M * N if out_bytes is None else out_bytes) + extra))
+        L.append((cls, M, N, K, 2 * M * cin + 2 * N * K + (2 * M * N if out_bytes is None else out_bytes) + extra, 2.0 * M * N * K))
     h = IMG // 2
     add("stem 7x7/2", B * h * h, 64, 147, 16)                       # space-to-depth image: 16 fp16 per output pixel
     h //= 2
     cin = 64
     for s, nb in enumerate({101: (3, 4, 23, 3), 50: (3, 4, 6, 3)}[architecture]):
         f = 64 << s
+        fusable = (not UNFUSED) and f <= 256            # csrc/conv_fused.cuh: A tile of the expansion <= 256 channels
         for i in range(nb):
             stride = 2 if (i == 0 and s > 0) else 1
             ho = h // stride
             m = B * ho * ho
-            add(f"res{s + 2} 2a 1x1", m, f, cin, cin)
+            if not (fusable and i > 0):                   # else: this block's reduction ran inside the previous block's fused launch
+                add(f"res{s + 2} 2a 1x1", m, f, cin, cin)
             add(f"res{s + 2} 2b 3x3", m, f, 9 * f, f)
             if i == 0:
                 add(f"res{s + 2} shortcut 1x1", m, 4 * f, cin, cin)
-            add(f"res{s + 2} 2c 1x1 + residual", m, 4 * f, f, f, extra=2 * m * 4 * f)
+            if fusable and i < nb - 1:
+                # expansion (+ residual) and the next block's reduction in one launch: X is written once and not read back
+                L.append((f"res{s + 2} 2c + next 2a (fused)", m, 4 * f, f,
+                          2 * m * f + 2 * m * 4 * f + 2 * m * 4 * f + 2 * m * f + 2 * 2 * (4 * f * f), 2.0 * m * (4 * f * f + f * 4 * f)))
+            else:
+                add(f"res{s + 2} 2c 1x1 + residual", m, 4 * f, f, f, extra=2 * m * 4 * f)
             h, cin = ho, 4 * f
     lv = [IMG // 4 >> l for l in range(5)]
     for l, c in zip((3, 2, 1, 0), (2048, 1024, 512, 256)):
@@ -84,7 +92,7 @@ def main():
     launches = list(by.values())
     start = next(i for i, d in enumerate(launches) if d["name"].startswith("preprocess_s2d"))
     launches = launches[start:] + launches[:start]          # the capture may start mid-step; a step begins at the pre-processing
-    convs = [d for d in launches if "conv_gemm_kernel" in d["name"]]
+    convs = [d for d in launches if "conv_gemm_kernel" in d["name"] or "conv_fused_expand_reduce_kernel" in d["name"]]
     layers = plan()
     assert len(convs) == len(layers), (len(convs), len(layers))
     peaks = {}
@@ -96,22 +104,25 @@ def main():
     hbm = float(peaks.get("hbm_gbs", 6462.7))
     step_ns = sum(d["gpu__time_duration.sum"] for d in launches)
     agg = collections.OrderedDict()
-    for d, (cls, M, N, K, alg_bytes) in zip(convs, layers):
-        bn, ctas = map(int, re.search(r"conv_gemm_kernel<(\d+), (\d+)>", d["name"]).groups())
+    for d, (cls, M, N, K, alg_bytes, fl) in zip(convs, layers):
+        mt = re.search(r"conv_gemm_kernel<(\d+), (\d+)>", d["name"])
+        fused = mt is None
+        assert fused == ("fused" in cls), (cls, d["name"])
+        bn, ctas = (N, 1) if fused else map(int, mt.groups())        # the fused kernel: one 128-pixel tile, all channels
         tiles = math.ceil(M / (128 * ctas)) * math.ceil(N / bn)
         units = 148 // ctas                                  # CTA pairs: 74 clusters
         a = agg.setdefault(cls, dict(n=0, ns=0.0, flops=0.0, tens=0.0, dram=0.0, alg=0.0, bound=0.0, membound=0, tiles=tiles, waves=tiles / units,
-                                     cfg=f"{128 * ctas}x{bn}"))
+                                     cfg="128xall" if fused else f"{128 * ctas}x{bn}"))
         a["n"] += 1
         a["ns"] += d["gpu__time_duration.sum"]
-        a["flops"] += 2.0 * M * N * K
+        a["flops"] += fl
         a["tens"] += d["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"] * d["gpu__time_duration.sum"]
         dram = d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"]
         a["dram"] += dram
         a["alg"] += alg_bytes
         # roofline of this launch: tensor time at the sustained peak vs the bytes it cannot avoid moving (L2-resident
         # operands make the measured DRAM bytes smaller than the algorithmic ones; wasted re-reads make them larger)
-        t_c, t_m = 2.0 * M * N * K / (peak * 1e3), min(alg_bytes, dram) / hbm
+        t_c, t_m = fl / (peak * 1e3), min(alg_bytes, dram) / hbm
         a["bound"] += max(t_c, t_m)
         a["membound"] += t_m > t_c
     conv_ns = sum(a["ns"] for a in agg.values())
