@@ -81,6 +81,13 @@ __device__ __forceinline__ void convert_subchunk(uint32_t t_addr, const float* b
   }
 }
 
+// debug event trace, same buffer layout as cg::trace_ev (role sections 0 producer, 1 MMA, 2 epilogue; tools/trace_fused.py)
+__device__ __forceinline__ TraceCursor ftrace_open(const FusedParams& p, int role) {
+  TraceCursor c; c.n = 0;
+  c.base = p.trace ? p.trace + ((size_t)blockIdx.x * 3 + role) * (2 * CG_TRACE_MAX + 2) : nullptr;
+  return c;
+}
+
 __device__ __forceinline__ void tile_coords(const FusedParams& p, int t, int& x0, int& y0, int& img) {
   x0 = (t % p.tiles_x) * p.tw;
   y0 = ((t / p.tiles_x) % p.tiles_y) * p.th;
@@ -202,12 +209,15 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
           if (++slot == kSlots) { slot = 0; sph ^= 1u; }
         }
       };
+      TraceCursor tc = ftrace_open(p, 1);
       for (int t = first; t < tiles; t += step, ++tl) {
         cg::mbar_wait(a_full, tl & 1u);
+        cg::trace_ev(tc, 3, (uint32_t)t);               // MMA: A tile landed
         for (int j = 0; j < NCH; ++j) {
           const int acc = j & 1;
           cg::mbar_wait(t1_empty(acc), (t1_uses[acc] & 1u) ^ 1u);
           ++t1_uses[acc];
+          cg::trace_ev(tc, 10, (uint32_t)j);             // MMA: acc1 buffer free, GEMM1(j) starts
           cg::tc_fence_after();
           const uint32_t d1 = tmem_base + (uint32_t)(acc * 128);
           for (int kb = 0; kb < KB1; kb += 2) {
@@ -225,8 +235,9 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
             if (++slot == kSlots) { slot = 0; sph ^= 1u; }
           }
           cg::umma_commit(t1_full(acc));
+          cg::trace_ev(tc, 11, (uint32_t)j);             // MMA: GEMM1(j) issued (weights landed)
           if (j == NCH - 1) cg::umma_commit(a_empty);           // the A tile is free once the last chunk's MMAs retire
-          if (j >= 1) mma2(j - 1);
+          if (j >= 1) { mma2(j - 1); cg::trace_ev(tc, 12, (uint32_t)(j - 1)); }     // MMA: GEMM2(j-1) issued (X chunk + weights landed)
         }
         mma2(NCH - 1);
         cg::umma_commit(t2_full);
@@ -304,6 +315,8 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
     uint32_t rpar = 0;                                 // bit b: parity of the X uses of buffer b
     uint32_t tl = 0;
     uint8_t* stg_gen = smem_raw + kStageOff;
+    TraceCursor tc = ftrace_open(p, 2);
+    if (warp != 2 || lane != 0) tc.base = nullptr;
     for (int t = first; t < tiles; t += step, ++tl) {
       for (int j = 0; j < NCH; ++j) {
         const int acc = j & 1;
@@ -311,6 +324,7 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
         cg::epi_bar_sync();                            // bias chunk staged (and everybody is past chunk j - 2's reads of this half)
         cg::mbar_wait(t1_full(acc), t1_uses[acc] & 1u);
         ++t1_uses[acc];
+        cg::trace_ev(tc, 5, (uint32_t)j);              // epilogue: acc1 ready
         cg::tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128);
         #pragma unroll 1
@@ -318,6 +332,7 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
           const int b = 2 * acc + s;
           cg::mbar_wait(r_full(b), (rpar >> b) & 1u);  // residual sub-chunk landed (so the buffer is free, too)
           rpar ^= 1u << b;
+          cg::trace_ev(tc, 9, (uint32_t)(2 * j + s));  // epilogue: residual sub-chunk landed
           convert_subchunk<true>(t_addr + (uint32_t)(s * 64), bias1_s + acc * 128 + s * 64, stg_gen + b * kStageBytes + row_off, sw, lo1);
           if (s == 1) {
             cg::tc_fence_before();
@@ -327,9 +342,11 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
           cg::fence_proxy_async_smem();                // generic-proxy writes -> visible to the TMA store and to the MMA
           __syncwarp();
           if (lane == 0) { cg::mbar_arrive(s_full(b)); cg::mbar_arrive(x_full(b)); }
+          cg::trace_ev(tc, 6, (uint32_t)(2 * j + s));  // epilogue: sub-chunk staged
         }
       }
       cg::mbar_wait(t2_full, tl & 1u);
+      cg::trace_ev(tc, 13, (uint32_t)t);               // epilogue: acc2 ready
       cg::tc_fence_after();
       const uint32_t t_addr2 = tmem_base + ((uint32_t)(q * 32) << 16) + 256u;
       #pragma unroll 1
@@ -344,6 +361,7 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
         cg::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) cg::mbar_arrive(s_full(y));
+        cg::trace_ev(tc, 14, (uint32_t)y);             // epilogue: Y sub-chunk staged
       }
     }
   }

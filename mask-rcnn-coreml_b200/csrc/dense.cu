@@ -396,6 +396,7 @@ MRCNN_API int mrcnn_debug_fused_expand_reduce(mrcnn_ctx* ctx, const void* a, int
   FusedPlan plan;
   int rc = fused_plan_build(ctx, e, r, &plan);
   if (rc) return rc;
+  plan.p.trace = g_trace_buf;
   return fused_plan_run(ctx, plan);
 }
 

@@ -62,6 +62,7 @@ struct FusedParams {
   int relu1, relu2;
   const float* bias1;          // [n1]
   const float* bias2;          // [n2]
+  unsigned long long* trace;   // debug event trace (layout of cg::trace_ev: 3 role sections per CTA), or null
 };
 struct FusedPlan {
   CUtensorMap tmA, tmB1, tmB2, tmR, tmX, tmY;
