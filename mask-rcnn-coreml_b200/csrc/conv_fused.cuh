@@ -43,7 +43,8 @@ static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA c
 
 // 64 accumulator columns of this thread's row -> (+bias, +residual already in the staging row, ReLU) -> fp16 -> staging row
 template <bool RES>
-__device__ __forceinline__ void convert_subchunk(uint32_t t_addr, const float* bias64, uint8_t* srow, uint32_t sw, __half2 lo2) {
+__device__ __forceinline__ void convert_subchunk(uint32_t t_addr, const float* bias64, uint8_t* srow, uint32_t sw, __half2 lo2,
+                                                 TraceCursor* tc = nullptr) {
   #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
     uint32_t v[32];
@@ -57,6 +58,7 @@ __device__ __forceinline__ void convert_subchunk(uint32_t t_addr, const float* b
       if (RES) rq[g] = *reinterpret_cast<const uint4*>(srow + ((((uint32_t)(hh * 4 + g)) ^ sw) << 4));
     }
     tmem_ld_wait();
+    if (tc) trace_ev(*tc, 15, (uint32_t)hh);           // debug: TMEM half landed
     #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float2 f[4];
@@ -95,6 +97,11 @@ __device__ __forceinline__ void tile_coords(const FusedParams& p, int t, int& x0
 }
 }  // namespace cgf
 
+// CTAS = 2: a CTA pair computes two adjacent pixel tiles with tcgen05.mma.cta_group::2 (M = 256, issued by the leader): each CTA
+// stages its own A tile, its own residual / X / Y sub-chunks and HALF of every weight tile, so the weight ring holds twice as many
+// K blocks -- with one CTA per tile the MMA warp waits for weights most of the time (128 KB per chunk through a 96 KB ring at the
+// ~4000 clk the L2 answers in under this load; tools/trace_fused.py).
+template <int CTAS>
 __global__ void __launch_bounds__(CG_THREADS, 1)
 conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
                                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmR,
@@ -125,55 +132,85 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB1 = p.c1 / 64, NCH = p.n1 / 128, NY = p.n2 / 64;
+  const uint32_t crank = (CTAS == 2) ? cg::cluster_ctarank() : 0u;          // rank in the pair; 0 = leader (issues the MMAs)
+  // barriers the leader's MMA thread waits on collect arrivals from both CTAs; TMA bytes of both CTAs land on the leader's barrier
+  auto arrive_leader = [&](uint32_t b) { if (CTAS == 2) cg::mbar_arrive_cluster(cg::mapa_rank(b, 0)); else cg::mbar_arrive(b); };
+  auto commit = [&](uint32_t b) { if (CTAS == 2) cg::umma_commit_2cta(b); else cg::umma_commit(b); };
   if (warp == 0 && lane == 0) {
     cg::prefetch_tmap(&tmA); cg::prefetch_tmap(&tmB1); cg::prefetch_tmap(&tmB2);
     cg::mbar_init(a_full, 1); cg::mbar_init(a_empty, 1);
     for (int s = 0; s < kSlots; ++s) { cg::mbar_init(b_full(s), 1); cg::mbar_init(b_empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { cg::mbar_init(t1_full(a), 1); cg::mbar_init(t1_empty(a), 4); }
-    cg::mbar_init(t2_full, 1); cg::mbar_init(t2_empty, 4);
+    for (int a = 0; a < 2; ++a) { cg::mbar_init(t1_full(a), 1); cg::mbar_init(t1_empty(a), 4 * CTAS); }
+    cg::mbar_init(t2_full, 1); cg::mbar_init(t2_empty, 4 * CTAS);
     for (int b = 0; b < 4; ++b) {
-      cg::mbar_init(r_full(b), 1); cg::mbar_init(s_full(b), 4); cg::mbar_init(x_full(b), 4); cg::mbar_init(x_done(b), 1);
+      cg::mbar_init(r_full(b), 1); cg::mbar_init(s_full(b), 4); cg::mbar_init(x_full(b), 4 * CTAS); cg::mbar_init(x_done(b), 1);
       cg::mbar_init(s_free(b), 1);
     }
     cg::fence_barrier_init();
   }
-  if (warp == 1) cg::tmem_alloc(tmem_slot, 512);
+  if (warp == 1) { if (CTAS == 2) cg::tmem_alloc_2cta(tmem_slot, 512); else cg::tmem_alloc(tmem_slot, 512); }
   cg::tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cg::cluster_sync_all();             // the peer's barriers are initialised before anything is signalled on them
   cg::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  const int tiles = p.n_img * p.tiles_y * p.tiles_x;
-  const int first = (int)blockIdx.x, step = (int)gridDim.x;
+  // work item w = first, first + step, ... < items: a tile (CTAS = 1) or a pair of adjacent tiles, of which this CTA owns tile
+  // CTAS * w + crank (the phantom tile of an odd count lies outside the tensor: TMA zero-fills its loads and clips its stores)
+  const int items = (p.n_img * p.tiles_y * p.tiles_x + CTAS - 1) / CTAS;
+  const int first = (int)blockIdx.x / CTAS, step = (int)gridDim.x / CTAS;
+  const int tiles = items;                            // loop bound of every role below
+  auto my_tile = [&](int w) { return CTAS * w + (int)crank; };
 
   if (warp == 0) {
     // ===================== producer =====================
     if (lane == 0) {
       int slot = 0; uint32_t sph = 0;
       uint32_t tl = 0;                                 // local tile counter
+      const uint32_t rows1 = 128u / CTAS, rows2 = (uint32_t)p.n2 / CTAS;     // rows of a W1 / W2 tile this CTA stages
       auto load_b2 = [&](int c) {
         for (int i = 0; i < 2; ++i) {
           cg::mbar_wait(b_empty(slot), sph ^ 1u);
-          cg::mbar_expect_tx(b_full(slot), (uint32_t)p.n2 * 128u);
-          cg::tma_load_2d(ring + (uint32_t)slot * kSlotBytes, &tmB2, b_full(slot), c * 128 + i * 64, 0);
+          const uint32_t dst = ring + (uint32_t)slot * kSlotBytes;
+          if (CTAS == 2) {
+            if (crank == 0) cg::mbar_expect_tx(b_full(slot), (uint32_t)p.n2 * 128u);
+            cg::tma_load_2d_2cta(dst, &tmB2, cg::mapa_rank(b_full(slot), 0), c * 128 + i * 64, (int)(crank * rows2));
+          } else {
+            cg::mbar_expect_tx(b_full(slot), (uint32_t)p.n2 * 128u);
+            cg::tma_load_2d(dst, &tmB2, b_full(slot), c * 128 + i * 64, 0);
+          }
           if (++slot == kSlots) { slot = 0; sph ^= 1u; }
         }
       };
       for (int t = first; t < tiles; t += step, ++tl) {
         int x0, y0, img;
-        tile_coords(p, t, x0, y0, img);
+        tile_coords(p, my_tile(t), x0, y0, img);
         cg::mbar_wait(a_empty, (tl & 1u) ^ 1u);
-        cg::mbar_expect_tx(a_full, (uint32_t)KB1 * kABytes);
-        for (int kb = 0; kb < KB1; ++kb) cg::tma_load_4d(a_base + (uint32_t)kb * kABytes, &tmA, a_full, kb * 64, x0, y0, img);
+        if (CTAS == 2) {
+          if (crank == 0) cg::mbar_expect_tx(a_full, (uint32_t)(2 * KB1) * kABytes);
+          const uint32_t lbar = cg::mapa_rank(a_full, 0);
+          for (int kb = 0; kb < KB1; ++kb) cg::tma_load_4d_2cta(a_base + (uint32_t)kb * kABytes, &tmA, lbar, kb * 64, x0, y0, img);
+        } else {
+          cg::mbar_expect_tx(a_full, (uint32_t)KB1 * kABytes);
+          for (int kb = 0; kb < KB1; ++kb) cg::tma_load_4d(a_base + (uint32_t)kb * kABytes, &tmA, a_full, kb * 64, x0, y0, img);
+        }
         for (int j = 0; j < NCH; ++j) {
           for (int kb = 0; kb < KB1; kb += 2) {
             const int nk = min(2, KB1 - kb);
             cg::mbar_wait(b_empty(slot), sph ^ 1u);
-            cg::mbar_expect_tx(b_full(slot), (uint32_t)nk * 16384u);
-            for (int i = 0; i < nk; ++i)
-              cg::tma_load_2d(ring + (uint32_t)slot * kSlotBytes + (uint32_t)i * 16384u, &tmB1, b_full(slot), (kb + i) * 64, j * 128);
+            // a slot holds two K blocks of the chunk's W1 rows: [K block kb][K block kb + 1], each rows1 x 128 B
+            if (CTAS == 2) {
+              if (crank == 0) cg::mbar_expect_tx(b_full(slot), (uint32_t)nk * 16384u);
+              const uint32_t lbar = cg::mapa_rank(b_full(slot), 0);
+              for (int i = 0; i < nk; ++i)
+                cg::tma_load_2d_2cta(ring + (uint32_t)slot * kSlotBytes + (uint32_t)i * 16384u, &tmB1, lbar, (kb + i) * 64, j * 128 + (int)(crank * rows1));
+            } else {
+              cg::mbar_expect_tx(b_full(slot), (uint32_t)nk * 16384u);
+              for (int i = 0; i < nk; ++i)
+                cg::tma_load_2d(ring + (uint32_t)slot * kSlotBytes + (uint32_t)i * 16384u, &tmB1, b_full(slot), (kb + i) * 64, j * 128);
+            }
             if (++slot == kSlots) { slot = 0; sph ^= 1u; }
           }
           if (j >= 1) load_b2(j - 1);
@@ -182,10 +219,13 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc1 = cg::make_idesc_f16(128, 128);
-      const uint32_t idesc2 = cg::make_idesc_f16(128, p.n2);
+    // ===================== MMA issuer (of the leader CTA in a pair) =====================
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc1 = cg::make_idesc_f16(128 * CTAS, 128);
+      const uint32_t idesc2 = cg::make_idesc_f16(128 * CTAS, p.n2);
+      auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t accum) {
+        if (CTAS == 2) cg::umma_f16_2cta(d, ad, bd, idesc, accum); else cg::umma_f16(d, ad, bd, idesc, accum);
+      };
       int slot = 0; uint32_t sph = 0;
       uint32_t tl = 0;
       uint32_t t1_uses[2] = {0, 0};
@@ -203,9 +243,9 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
           const uint64_t bdesc = cg::make_sw128_desc(ring + (uint32_t)slot * kSlotBytes);
           #pragma unroll
           for (int k = 0; k < 4; ++k)
-            cg::umma_f16(acc2, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (c | i | k) ? 1u : 0u);
-          cg::umma_commit(b_empty(slot));
-          cg::umma_commit(x_done(b));
+            mma(acc2, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (c | i | k) ? 1u : 0u);
+          commit(b_empty(slot));
+          commit(x_done(b));
           if (++slot == kSlots) { slot = 0; sph ^= 1u; }
         }
       };
@@ -229,18 +269,18 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
               const uint64_t bdesc = cg::make_sw128_desc(ring + (uint32_t)slot * kSlotBytes + (uint32_t)i * 16384u);
               #pragma unroll
               for (int k = 0; k < 4; ++k)
-                cg::umma_f16(d1, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, ((kb + i) | k) ? 1u : 0u);
+                mma(d1, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, ((kb + i) | k) ? 1u : 0u);
             }
-            cg::umma_commit(b_empty(slot));
+            commit(b_empty(slot));
             if (++slot == kSlots) { slot = 0; sph ^= 1u; }
           }
-          cg::umma_commit(t1_full(acc));
+          commit(t1_full(acc));
           cg::trace_ev(tc, 11, (uint32_t)j);             // MMA: GEMM1(j) issued (weights landed)
-          if (j == NCH - 1) cg::umma_commit(a_empty);           // the A tile is free once the last chunk's MMAs retire
+          if (j == NCH - 1) commit(a_empty);                    // the A tile is free once the last chunk's MMAs retire
           if (j >= 1) { mma2(j - 1); cg::trace_ev(tc, 12, (uint32_t)(j - 1)); }     // MMA: GEMM2(j-1) issued (X chunk + weights landed)
         }
         mma2(NCH - 1);
-        cg::umma_commit(t2_full);
+        commit(t2_full);
       }
     }
   } else if (warp == 6) {
@@ -251,7 +291,7 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
       auto load_residual = [&](int tl, int j, int s) {        // chunk j, sub-chunk s of local tile tl -> buffer 2 * (j & 1) + s
         if (tl >= my_tiles) return;
         int x0, y0, img;
-        tile_coords(p, first + tl * step, x0, y0, img);
+        tile_coords(p, my_tile(first + tl * step), x0, y0, img);
         const int b = 2 * (j & 1) + s;
         cg::mbar_expect_tx(r_full(b), (uint32_t)kStageBytes);
         cg::tma_load_4d(stg + (uint32_t)b * kStageBytes, &tmR, r_full(b), j * 128 + s * 64, x0, y0, img);
@@ -274,7 +314,7 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
       };
       for (int tl = 0; tl < my_tiles; ++tl) {
         int x0, y0, img;
-        tile_coords(p, first + tl * step, x0, y0, img);
+        tile_coords(p, my_tile(first + tl * step), x0, y0, img);
         for (int j = 0; j < NCH; ++j)
           for (int s = 0; s < 2; ++s) {
             const int b = 2 * (j & 1) + s;
@@ -333,15 +373,16 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
           cg::mbar_wait(r_full(b), (rpar >> b) & 1u);  // residual sub-chunk landed (so the buffer is free, too)
           rpar ^= 1u << b;
           cg::trace_ev(tc, 9, (uint32_t)(2 * j + s));  // epilogue: residual sub-chunk landed
-          convert_subchunk<true>(t_addr + (uint32_t)(s * 64), bias1_s + acc * 128 + s * 64, stg_gen + b * kStageBytes + row_off, sw, lo1);
+          convert_subchunk<true>(t_addr + (uint32_t)(s * 64), bias1_s + acc * 128 + s * 64, stg_gen + b * kStageBytes + row_off, sw, lo1, &tc);
+          cg::trace_ev(tc, 16, (uint32_t)(2 * j + s)); // debug: converted
           if (s == 1) {
             cg::tc_fence_before();
             __syncwarp();
-            if (lane == 0) cg::mbar_arrive(t1_empty(acc));
+            if (lane == 0) arrive_leader(t1_empty(acc));
           }
           cg::fence_proxy_async_smem();                // generic-proxy writes -> visible to the TMA store and to the MMA
           __syncwarp();
-          if (lane == 0) { cg::mbar_arrive(s_full(b)); cg::mbar_arrive(x_full(b)); }
+          if (lane == 0) { cg::mbar_arrive(s_full(b)); arrive_leader(x_full(b)); }
           cg::trace_ev(tc, 6, (uint32_t)(2 * j + s));  // epilogue: sub-chunk staged
         }
       }
@@ -356,7 +397,7 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
         if (y == NY - 1) {
           cg::tc_fence_before();
           __syncwarp();
-          if (lane == 0) cg::mbar_arrive(t2_empty);
+          if (lane == 0) arrive_leader(t2_empty);
         }
         cg::fence_proxy_async_smem();
         __syncwarp();
@@ -365,7 +406,12 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
       }
     }
   }
+  // nobody leaves (or frees TMEM) while the partner may still read this CTA's smem / signal its barriers
   cg::tc_fence_before();
   __syncthreads();
-  if (warp == 1) { cg::tc_fence_after(); cg::tmem_dealloc(tmem_base, 512); }
+  if (CTAS == 2) cg::cluster_sync_all();
+  if (warp == 1) {
+    cg::tc_fence_after();
+    if (CTAS == 2) cg::tmem_dealloc_2cta(tmem_base, 512); else cg::tmem_dealloc(tmem_base, 512);
+  }
 }

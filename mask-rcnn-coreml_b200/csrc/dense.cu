@@ -324,34 +324,51 @@ int fused_plan_build(mrcnn_ctx* ctx, const ConvLaunch& e, const ConvLaunch& r, F
   if ((rc = encode_act_map(ctx, enc, &plan->tmR, e.residual, p.n1, p.n_img, p.h, p.w, p.tw, p.th, "R"))) return rc;
   if ((rc = encode_act_map(ctx, enc, &plan->tmX, e.out, p.n1, p.n_img, p.h, p.w, p.tw, p.th, "X"))) return rc;
   if ((rc = encode_act_map(ctx, enc, &plan->tmY, r.out, p.n2, p.n_img, p.h, p.w, p.tw, p.th, "Y"))) return rc;
-  if ((rc = encode_weight_map(ctx, enc, &plan->tmB1, e.w, p.c1, p.n1, 128, "W1"))) return rc;
-  if ((rc = encode_weight_map(ctx, enc, &plan->tmB2, r.w, p.n1, p.n2, p.n2, "W2"))) return rc;
-  const long tiles = (long)p.n_img * p.tiles_x * p.tiles_y, slots = ctx->sm_count;
-  const long rounds = (tiles + slots - 1) / slots;
-  plan->grid = (int)((tiles + rounds - 1) / rounds);              // balanced grid (see conv_plan_build)
+  const long tiles = (long)p.n_img * p.tiles_x * p.tiles_y;
+  {
+    static int env_ctas = -1;
+    // CTA pairs halve the weight bytes per CTA, but measured slower (862-868 vs 944-951 images/s): the epilogue's remote
+    // arrivals on the leader's barriers (one per sub-chunk per warp) stretch a sub-chunk from ~800 to 2000-5000 clk
+    // (tools/trace_fused.py).  Kept as an option (bit-identical, tested), off by default.
+    if (env_ctas < 0) { const char* ev = getenv("MRCNN_FUSE_CTAS"); env_ctas = ev ? atoi(ev) : 1; }
+    plan->ctas = (env_ctas == 2 && tiles >= 2) ? 2 : 1;
+  }
+  const int ctas = plan->ctas;
+  if ((rc = encode_weight_map(ctx, enc, &plan->tmB1, e.w, p.c1, p.n1, 128 / ctas, "W1"))) return rc;
+  if ((rc = encode_weight_map(ctx, enc, &plan->tmB2, r.w, p.n1, p.n2, p.n2 / ctas, "W2"))) return rc;
+  const long items = (tiles + ctas - 1) / ctas, slots = ctx->sm_count / ctas;
+  const long rounds = (items + slots - 1) / slots;
+  plan->grid = (int)(((items + rounds - 1) / rounds) * ctas);     // balanced grid (see conv_plan_build)
   const double px = (double)p.n_img * p.h * p.w;
   plan->flops = 2.0 * px * ((double)p.n1 * p.c1 + (double)p.n2 * p.n1);
   return MRCNN_OK;
 }
 
-int fused_plan_run(mrcnn_ctx* ctx, const FusedPlan& plan) {
+template <int CTAS>
+static int fused_launch(mrcnn_ctx* ctx, const FusedPlan& plan) {
   static bool attr_done[64] = {false};
   const int dv = ctx->device & 63;
   if (!attr_done[dv]) {
-    MRCNN_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_fused_expand_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cgf::kSmemBytes));
+    MRCNN_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_fused_expand_reduce_kernel<CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, cgf::kSmemBytes));
     attr_done[dv] = true;
   }
   ProfScope ps(ctx, PROF_CONV_GEMM, plan.flops);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(plan.grid); cfg.blockDim = dim3(CG_THREADS);
   cfg.dynamicSmemBytes = cgf::kSmemBytes; cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  MRCNN_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, conv_fused_expand_reduce_kernel, plan.tmA, plan.tmB1, plan.tmB2, plan.tmR, plan.tmX, plan.tmY, plan.p));
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = CTAS == 2 ? 2 : 1;
+  MRCNN_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, conv_fused_expand_reduce_kernel<CTAS>, plan.tmA, plan.tmB1, plan.tmB2, plan.tmR, plan.tmX, plan.tmY, plan.p));
   MRCNN_LAUNCH_CHECK(ctx);
   return MRCNN_OK;
+}
+
+int fused_plan_run(mrcnn_ctx* ctx, const FusedPlan& plan) {
+  return plan.ctas == 2 ? fused_launch<2>(ctx, plan) : fused_launch<1>(ctx, plan);
 }
 
 static unsigned long long* g_trace_buf = nullptr;   // set by mrcnn_debug_conv_trace; picked up by the conv2d hook only

@@ -67,7 +67,7 @@ struct FusedParams {
 struct FusedPlan {
   CUtensorMap tmA, tmB1, tmB2, tmR, tmX, tmY;
   FusedParams p;
-  int grid = 0;
+  int grid = 0, ctas = 1;      // ctas = 2: CTA pairs (tcgen05.mma.cta_group::2), each CTA stages half of every weight tile
   double flops = 0;
 };
 bool fused_plan_supported(const ConvLaunch& expand, const ConvLaunch& reduce);

@@ -147,6 +147,7 @@ FUSED_CASES = [
     (4, 64, 128, 64, 256, 64),         # several tiles per CTA with one Y sub-chunk (the store thread frees it at the tile's end)
     (8, 64, 96, 128, 512, 128),        # several tiles per CTA, two Y sub-chunks
     (8, 128, 128, 256, 1024, 256),     # seven tiles per CTA
+    (1, 24, 16, 128, 512, 128),        # three tiles: the second CTA pair owns a phantom tile
 ]
 
 
@@ -179,3 +180,41 @@ def test_fused_expand_reduce_bit_identical(pkg, ctx, case):
     ctx.synchronize()
     assert torch.equal(x, x_ref), f"X differs in {(x != x_ref).sum().item()} of {x.numel()} elements"
     assert torch.equal(y, y_ref), f"Y differs in {(y != y_ref).sum().item()} of {y.numel()} elements"
+
+
+def test_fused_expand_reduce_cta_pair_variant():
+    """MRCNN_FUSE_CTAS=2 (the fused kernel on CTA pairs, tcgen05.mma.cta_group::2; off by default): same bits as the
+    single-CTA variant.  The knob is read once per process, so the variant runs in its own interpreter."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = r'''
+import sys, zlib
+sys.path.insert(0, %r)
+import numpy as np, torch
+import maskrcnn_b200 as m
+ctx = m.Context()
+crc = 0
+for (n, h, w, c1, n1, n2) in [(8, 64, 64, 256, 1024, 256), (1, 24, 16, 128, 512, 128), (4, 64, 128, 64, 256, 64)]:
+    g = torch.Generator(device="cpu").manual_seed(11)
+    a = torch.randn(n, h, w, c1, generator=g).half().cuda()
+    w1 = (torch.randn(n1, c1, generator=g) / np.sqrt(c1)).half().cuda(); b1 = torch.randn(n1, generator=g).cuda()
+    res = torch.randn(n, h, w, n1, generator=g).half().cuda()
+    w2 = (torch.randn(n2, n1, generator=g) / np.sqrt(n1)).half().cuda(); b2 = torch.randn(n2, generator=g).cuda()
+    x = torch.zeros((n, h, w, n1), dtype=torch.float16, device="cuda"); y = torch.zeros((n, h, w, n2), dtype=torch.float16, device="cuda")
+    torch.cuda.synchronize()
+    m._cabi.check(ctx.handle, m.lib().mrcnn_debug_fused_expand_reduce(ctx.handle, a.data_ptr(), n, h, w, c1, w1.data_ptr(), b1.data_ptr(), n1,
+                                                                        res.data_ptr(), w2.data_ptr(), b2.data_ptr(), n2, x.data_ptr(), y.data_ptr()))
+    ctx.synchronize()
+    crc = zlib.crc32(y.cpu().numpy().tobytes(), zlib.crc32(x.cpu().numpy().tobytes(), crc))
+print("CRC", crc)
+''' % root
+    crcs = {}
+    for ctas in ("1", "2"):
+        e = dict(os.environ)
+        e["MRCNN_FUSE_CTAS"] = ctas
+        p = subprocess.run([sys.executable, "-c", script], env=e, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        crcs[ctas] = [ln for ln in p.stdout.splitlines() if ln.startswith("CRC")][-1]
+    assert crcs["1"] == crcs["2"], crcs

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import maskrcnn_b200 as m
 
 NAMES = {3: "M.a_landed", 10: "M.gemm1_start", 11: "M.gemm1_issued", 12: "M.gemm2_issued", 5: "E.acc1_ready", 9: "E.res_landed",
-         6: "E.sub_staged", 13: "E.acc2_ready", 14: "E.y_staged"}
+         6: "E.sub_staged", 15: "E.tmem_half", 16: "E.converted", 13: "E.acc2_ready", 14: "E.y_staged"}
 
 
 def main():
