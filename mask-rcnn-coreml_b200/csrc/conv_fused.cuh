@@ -32,11 +32,11 @@ namespace cgf {
 using namespace cg;
 
 constexpr int kABytes = 16384;                       // one K block of the A tile: 128 pixels x 64 channels
-constexpr int kSlotBytes = 32768;                    // weight ring slot
-constexpr int kSlots = 3;
+constexpr int kRingBytes = 98304;                    // weight ring: 3 slots of 32 KB (one CTA per tile) or 6 of 16 KB (CTA pairs: a
+                                                     // CTA stages half of every weight tile, so the same bytes hold twice the K blocks)
 constexpr int kStageBytes = 16384;                   // staging buffer: 128 pixels x 64 channels
-constexpr int kAOff = 0, kRingOff = 4 * kABytes, kStageOff = kRingOff + kSlots * kSlotBytes, kBarOff = kStageOff + 4 * kStageBytes;
-constexpr int kBarBytes = 320;
+constexpr int kAOff = 0, kRingOff = 4 * kABytes, kStageOff = kRingOff + kRingBytes, kBarOff = kStageOff + 4 * kStageBytes;
+constexpr int kBarBytes = 384;
 constexpr int kBiasOff = kBarOff + kBarBytes;        // bias1 chunk (2 x 128 floats) + bias2 (256 floats)
 constexpr int kSmemBytes = kBiasOff + (2 * 128 + 256) * 4;
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
@@ -112,38 +112,45 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
   const uint32_t smem_base = cg::smem_u32(smem_raw);
   if (smem_base & 1023u) __trap();                   // the layout has no slack for re-alignment: dynamic smem starts 1024-aligned
   const uint32_t a_base = smem_base + kAOff, ring = smem_base + kRingOff, stg = smem_base + kStageOff, bar = smem_base + kBarOff;
-  // barriers: a_full @0, a_empty @8, b_full[3] @16, b_empty[3] @40, t1_full[2] @64, t1_empty[2] @80, t2_full @96, t2_empty @104,
-  // r_full[4] @112, s_full[4] @144, x_full[4] @176, x_done[4] @208, s_free[4] @240, TMEM base slot @272 (block of kBarBytes = 320)
+  // barriers: a_full @0, a_empty @8, b_full[6] @16, b_empty[6] @64, t1_full[2] @112, t1_empty[2] @128, t2_full @144, t2_empty @152,
+  // r_full[4] @160, s_full[4] @192, x_full[4] @224, x_done[4] @256, s_free[4] @288; CTA pairs, on the leader: c_peer[2] @320 (the
+  // peer has drained acc1 #p and staged its X chunk), t2e_peer @336 (the peer has drained acc2) -- one remote arrival each, made
+  // by the peer's relay thread; TMEM base slot @344 (block of kBarBytes = 384)
   const uint32_t a_full = bar, a_empty = bar + 8;
   auto b_full = [&](int s) { return bar + 16u + 8u * s; };
-  auto b_empty = [&](int s) { return bar + 40u + 8u * s; };
-  auto t1_full = [&](int a) { return bar + 64u + 8u * a; };
-  auto t1_empty = [&](int a) { return bar + 80u + 8u * a; };
-  const uint32_t t2_full = bar + 96, t2_empty = bar + 104;
-  auto r_full = [&](int b) { return bar + 112u + 8u * b; };
-  auto s_full = [&](int b) { return bar + 144u + 8u * b; };
-  auto x_full = [&](int b) { return bar + 176u + 8u * b; };
-  auto x_done = [&](int b) { return bar + 208u + 8u * b; };
-  auto s_free = [&](int b) { return bar + 240u + 8u * b; };
-  const uint32_t tmem_slot = bar + 272u;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + kBarOff + 272);
+  auto b_empty = [&](int s) { return bar + 64u + 8u * s; };
+  auto t1_full = [&](int a) { return bar + 112u + 8u * a; };
+  auto t1_empty = [&](int a) { return bar + 128u + 8u * a; };
+  const uint32_t t2_full = bar + 144, t2_empty = bar + 152;
+  auto r_full = [&](int b) { return bar + 160u + 8u * b; };
+  auto s_full = [&](int b) { return bar + 192u + 8u * b; };
+  auto x_full = [&](int b) { return bar + 224u + 8u * b; };
+  auto x_done = [&](int b) { return bar + 256u + 8u * b; };
+  auto s_free = [&](int b) { return bar + 288u + 8u * b; };
+  auto c_peer = [&](int a) { return bar + 320u + 8u * a; };
+  const uint32_t t2e_peer = bar + 336u;
+  const uint32_t tmem_slot = bar + 344u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + kBarOff + 344);
   float* bias1_s = reinterpret_cast<float*>(smem_raw + kBiasOff);             // [2][128]
   float* bias2_s = bias1_s + 256;                                              // [n2 <= 256]
 
+  constexpr int kSlots = 3 * CTAS;
+  constexpr uint32_t kSlotBytes = 32768u / CTAS, kHalfSlot = kSlotBytes / 2;     // a W1 slot = two K blocks, kHalfSlot apart
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB1 = p.c1 / 64, NCH = p.n1 / 128, NY = p.n2 / 64;
   const uint32_t crank = (CTAS == 2) ? cg::cluster_ctarank() : 0u;          // rank in the pair; 0 = leader (issues the MMAs)
-  // barriers the leader's MMA thread waits on collect arrivals from both CTAs; TMA bytes of both CTAs land on the leader's barrier
-  auto arrive_leader = [&](uint32_t b) { if (CTAS == 2) cg::mbar_arrive_cluster(cg::mapa_rank(b, 0)); else cg::mbar_arrive(b); };
+  // TMA bytes of both CTAs land on the leader's barriers.  The epilogue warps arrive on LOCAL barriers only: a remote
+  // mbarrier.arrive.release.cluster costs the issuing warp ~1900 clk (tools/trace_fused.py), so the peer's completions are
+  // forwarded to the leader by a relay thread (the peer's otherwise idle MMA warp), one remote arrival per X chunk.
   auto commit = [&](uint32_t b) { if (CTAS == 2) cg::umma_commit_2cta(b); else cg::umma_commit(b); };
   if (warp == 0 && lane == 0) {
     cg::prefetch_tmap(&tmA); cg::prefetch_tmap(&tmB1); cg::prefetch_tmap(&tmB2);
     cg::mbar_init(a_full, 1); cg::mbar_init(a_empty, 1);
     for (int s = 0; s < kSlots; ++s) { cg::mbar_init(b_full(s), 1); cg::mbar_init(b_empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { cg::mbar_init(t1_full(a), 1); cg::mbar_init(t1_empty(a), 4 * CTAS); }
-    cg::mbar_init(t2_full, 1); cg::mbar_init(t2_empty, 4 * CTAS);
+    for (int a = 0; a < 2; ++a) { cg::mbar_init(t1_full(a), 1); cg::mbar_init(t1_empty(a), 4); cg::mbar_init(c_peer(a), 1); }
+    cg::mbar_init(t2_full, 1); cg::mbar_init(t2_empty, 4); cg::mbar_init(t2e_peer, 1);
     for (int b = 0; b < 4; ++b) {
-      cg::mbar_init(r_full(b), 1); cg::mbar_init(s_full(b), 4); cg::mbar_init(x_full(b), 4 * CTAS); cg::mbar_init(x_done(b), 1);
+      cg::mbar_init(r_full(b), 1); cg::mbar_init(s_full(b), 4); cg::mbar_init(x_full(b), 4); cg::mbar_init(x_done(b), 1);
       cg::mbar_init(s_free(b), 1);
     }
     cg::fence_barrier_init();
@@ -205,11 +212,11 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
               if (crank == 0) cg::mbar_expect_tx(b_full(slot), (uint32_t)nk * 16384u);
               const uint32_t lbar = cg::mapa_rank(b_full(slot), 0);
               for (int i = 0; i < nk; ++i)
-                cg::tma_load_2d_2cta(ring + (uint32_t)slot * kSlotBytes + (uint32_t)i * 16384u, &tmB1, lbar, (kb + i) * 64, j * 128 + (int)(crank * rows1));
+                cg::tma_load_2d_2cta(ring + (uint32_t)slot * kSlotBytes + (uint32_t)i * kHalfSlot, &tmB1, lbar, (kb + i) * 64, j * 128 + (int)(crank * rows1));
             } else {
               cg::mbar_expect_tx(b_full(slot), (uint32_t)nk * 16384u);
               for (int i = 0; i < nk; ++i)
-                cg::tma_load_2d(ring + (uint32_t)slot * kSlotBytes + (uint32_t)i * 16384u, &tmB1, b_full(slot), (kb + i) * 64, j * 128);
+                cg::tma_load_2d(ring + (uint32_t)slot * kSlotBytes + (uint32_t)i * kHalfSlot, &tmB1, b_full(slot), (kb + i) * 64, j * 128);
             }
             if (++slot == kSlots) { slot = 0; sph ^= 1u; }
           }
@@ -231,8 +238,17 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
       uint32_t t1_uses[2] = {0, 0};
       uint32_t xpar = 0;                               // bit b: parity of the X uses of staging buffer b consumed so far
       const uint32_t acc2 = tmem_base + 256u;
+      uint32_t cp_uses[2] = {0, 0};
       auto mma2 = [&](int c) {
-        if (c == 0) { cg::mbar_wait(t2_empty, (tl & 1u) ^ 1u); cg::tc_fence_after(); }
+        if (c == 0) {
+          cg::mbar_wait(t2_empty, (tl & 1u) ^ 1u);
+          if (CTAS == 2) cg::mbar_wait(t2e_peer, (tl & 1u) ^ 1u);
+          cg::tc_fence_after();
+        }
+        if (CTAS == 2) {                                // the peer's half of X chunk c is staged (and its acc1 buffer drained)
+          cg::mbar_wait(c_peer(c & 1), cp_uses[c & 1] & 1u);
+          ++cp_uses[c & 1];
+        }
         for (int i = 0; i < 2; ++i) {
           const int b = 2 * (c & 1) + i;
           cg::mbar_wait(x_full(b), (xpar >> b) & 1u);
@@ -266,7 +282,7 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
             cg::tc_fence_after();
             for (int i = 0; i < nk; ++i) {
               const uint64_t adesc = cg::make_sw128_desc(a_base + (uint32_t)(kb + i) * kABytes);
-              const uint64_t bdesc = cg::make_sw128_desc(ring + (uint32_t)slot * kSlotBytes + (uint32_t)i * 16384u);
+              const uint64_t bdesc = cg::make_sw128_desc(ring + (uint32_t)slot * kSlotBytes + (uint32_t)i * kHalfSlot);
               #pragma unroll
               for (int k = 0; k < 4; ++k)
                 mma(d1, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, ((kb + i) | k) ? 1u : 0u);
@@ -281,6 +297,21 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
         }
         mma2(NCH - 1);
         commit(t2_full);
+      }
+    }
+    if (CTAS == 2 && lane == 0 && crank == 1) {
+      // ===================== relay (peer CTA): local completions -> one remote arrival on the leader's barriers =====================
+      uint32_t xpar = 0;
+      uint32_t tl = 0;
+      for (int t = first; t < tiles; t += step, ++tl) {
+        for (int j = 0; j < NCH; ++j) {
+          const int b = 2 * (j & 1) + 1;                // the chunk's second sub-chunk: every warp arrives there last
+          cg::mbar_wait(x_full(b), (xpar >> b) & 1u);
+          xpar ^= 1u << b;
+          cg::mbar_arrive_cluster(cg::mapa_rank(c_peer(j & 1), 0));
+        }
+        cg::mbar_wait(t2_empty, tl & 1u);
+        cg::mbar_arrive_cluster(cg::mapa_rank(t2e_peer, 0));
       }
     }
   } else if (warp == 6) {
@@ -378,11 +409,11 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
           if (s == 1) {
             cg::tc_fence_before();
             __syncwarp();
-            if (lane == 0) arrive_leader(t1_empty(acc));
+            if (lane == 0) cg::mbar_arrive(t1_empty(acc));
           }
           cg::fence_proxy_async_smem();                // generic-proxy writes -> visible to the TMA store and to the MMA
           __syncwarp();
-          if (lane == 0) { cg::mbar_arrive(s_full(b)); arrive_leader(x_full(b)); }
+          if (lane == 0) { cg::mbar_arrive(s_full(b)); cg::mbar_arrive(x_full(b)); }
           cg::trace_ev(tc, 6, (uint32_t)(2 * j + s));  // epilogue: sub-chunk staged
         }
       }
@@ -397,7 +428,7 @@ conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const _
         if (y == NY - 1) {
           cg::tc_fence_before();
           __syncwarp();
-          if (lane == 0) arrive_leader(t2_empty);
+          if (lane == 0) cg::mbar_arrive(t2_empty);
         }
         cg::fence_proxy_async_smem();
         __syncwarp();

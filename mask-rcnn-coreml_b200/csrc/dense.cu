@@ -327,9 +327,9 @@ int fused_plan_build(mrcnn_ctx* ctx, const ConvLaunch& e, const ConvLaunch& r, F
   const long tiles = (long)p.n_img * p.tiles_x * p.tiles_y;
   {
     static int env_ctas = -1;
-    // CTA pairs halve the weight bytes per CTA, but measured slower (862-868 vs 944-951 images/s): the epilogue's remote
-    // arrivals on the leader's barriers (one per sub-chunk per warp) stretch a sub-chunk from ~800 to 2000-5000 clk
-    // (tools/trace_fused.py).  Kept as an option (bit-identical, tested), off by default.
+    // CTA pairs halve the weight bytes per CTA and shorten the chunk period in isolation (4150-4700 vs 5000-5250 clk,
+    // tools/trace_fused.py), but the step does not follow: 944 / 928 vs 951 / 954 images/s.  Kept as an option
+    // (bit-identical, tested), off by default.
     if (env_ctas < 0) { const char* ev = getenv("MRCNN_FUSE_CTAS"); env_ctas = ev ? atoi(ev) : 1; }
     plan->ctas = (env_ctas == 2 && tiles >= 2) ? 2 : 1;
   }
