@@ -14,11 +14,11 @@
 // staging buffers = two K blocks of the second GEMM, which accumulates all chunks into a third, n2-column accumulator:
 //
 //   TMEM (512 columns)   [acc1 #0: 128][acc1 #1: 128][acc2: n2 <= 256]
-//   shared memory        A tile (c1/64 K blocks x 16 KB, resident for the tile) | weight ring 3 x 32 KB (a slot = two
-//                        K blocks of W1 for one chunk, or one K block of W2) | 4 staging buffers x 16 KB
+//   shared memory        A tile (c1/64 K blocks x 16 KB, resident for the tile) | weight ring 96 KB (a slot = two K blocks
+//                        of W1 for one chunk, or one K block of W2) | 4 staging buffers x 16 KB | barriers, bias
 //   warp 0  producer     A tile, then the weight slots in the order the MMA warp consumes them
 //   warp 1  MMA issuer   GEMM1(j) ... GEMM1(j+1), GEMM2(j), ...: the second GEMM lags one chunk so that the epilogue of
-//                        chunk j overlaps the MMAs of chunk j + 1
+//                        chunk j overlaps the MMAs of chunk j + 1  (CTA pairs: the leader's; the peer's is the relay thread)
 //   warps 2-5 epilogue   chunk j: TMEM -> +bias +residual, ReLU, fp16 -> staging (in place over the TMA-loaded residual);
 //                        after the last chunk: acc2 -> +bias, ReLU -> staging (Y)
 //   warp 6  store thread TMA stores of X / Y sub-chunks; frees a buffer when its store has read it AND the second GEMM has
@@ -100,7 +100,8 @@ __device__ __forceinline__ void tile_coords(const FusedParams& p, int t, int& x0
 // CTAS = 2: a CTA pair computes two adjacent pixel tiles with tcgen05.mma.cta_group::2 (M = 256, issued by the leader): each CTA
 // stages its own A tile, its own residual / X / Y sub-chunks and HALF of every weight tile, so the weight ring holds twice as many
 // K blocks -- with one CTA per tile the MMA warp waits for weights most of the time (128 KB per chunk through a 96 KB ring at the
-// ~4000 clk the L2 answers in under this load; tools/trace_fused.py).
+// ~4000 clk the L2 answers in under this load; tools/trace_fused.py).  Measured: shorter chunk period in isolation, no gain in
+// the pipeline (end): the host launches CTAS = 1 unless MRCNN_FUSE_CTAS=2.
 template <int CTAS>
 __global__ void __launch_bounds__(CG_THREADS, 1)
 conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
