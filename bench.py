@@ -458,7 +458,7 @@ class PipelineWorkload:
         ms, n, work = prof["conv_gemm_tcgen05"]
         ach = work / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         peak = peaks["bf16_sustained"]
-        return {"kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM convolution, every dense layer)", "bound": "tensor",
+        return {"kernel": "conv_gemm_kernel + conv_fused_expand_reduce_kernel (tcgen05 implicit-GEMM convolutions: every dense layer)", "bound": "tensor",
                 "achieved": ach, "peak": peak, "peak_source": peaks["source"] + " (sustained cuBLAS bf16; fp16 runs at the same rate)",
                 "unit": "TFLOP/s", "frac": ach / peak, "traffic": load_traffic("conv_gemm_tcgen05"), "traffic_unit": "B/launch (ncu dram bytes, profiles/traffic_r2.json)",
                 "launches": n, "avg_launch_ms": ms / max(n, 1), "algorithmic_flops_per_launch": work / max(n, 1)}
