@@ -125,7 +125,14 @@ MRCNN_API void mrcnn_destroy(mrcnn_ctx* ctx);
 MRCNN_API const char* mrcnn_last_error(const mrcnn_ctx* ctx);
 
 /* Use an externally owned CUDA stream (cudaStream_t / CUstream as void*) for
- * all work of this context; NULL restores the context's own stream. */
+ * all work of this context; NULL restores the context's own stream.
+ * Ordering contract for DEVICE pointers: the context's own stream is created
+ * cudaStreamNonBlocking, i.e. it is NOT ordered with the legacy default stream
+ * or with any other stream.  Work that produces an input buffer (or still reads
+ * an output buffer) on another stream must have completed, or be ordered by the
+ * caller (event / stream synchronisation, or by handing that stream to
+ * mrcnn_set_stream), before the call.  Calls with host pointers synchronise
+ * the context's stream before they return. */
 MRCNN_API int mrcnn_set_stream(mrcnn_ctx* ctx, void* cuda_stream);
 MRCNN_API int mrcnn_synchronize(mrcnn_ctx* ctx);
 
