@@ -124,6 +124,12 @@ def ptr(x, dtype=None, count=None):
             raise MaskRCNNError(EINVAL, f"tensor must be {dtype}, got {x.dtype}")
         if count is not None and x.numel() < count:
             raise MaskRCNNError(EINVAL, f"tensor has {x.numel()} elements, {count} needed")
+        if x.is_cuda:
+            # The context's stream is non-blocking (include/maskrcnn_cuda.h, mrcnn_set_stream): whatever PyTorch has queued on
+            # its current stream for this device (the kernels that produce this tensor, or still read it) must be done
+            # before the library touches the buffer.  A host-side wait on an idle stream costs microseconds.
+            import torch
+            torch.cuda.current_stream(x.device).synchronize()
         return C.c_void_p(x.data_ptr())
     if hasattr(x, "ctypes"):              # numpy.ndarray
         if not x.flags["C_CONTIGUOUS"]:
