@@ -101,7 +101,7 @@ __device__ __forceinline__ void tile_coords(const FusedParams& p, int t, int& x0
 // stages its own A tile, its own residual / X / Y sub-chunks and HALF of every weight tile, so the weight ring holds twice as many
 // K blocks -- with one CTA per tile the MMA warp waits for weights most of the time (128 KB per chunk through a 96 KB ring at the
 // ~4000 clk the L2 answers in under this load; tools/trace_fused.py).  Measured: shorter chunk period in isolation, no gain in
-// the pipeline (end): the host launches CTAS = 1 unless MRCNN_FUSE_CTAS=2.
+// the pipeline ("Kept"): the host launches CTAS = 1 unless MRCNN_FUSE_CTAS=2.
 template <int CTAS>
 __global__ void __launch_bounds__(CG_THREADS, 1)
 conv_fused_expand_reduce_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
